@@ -1,0 +1,51 @@
+// Host side of the tcgen05 attention kernel + C entry point f5_attention.
+#include "attn.cuh"
+#include "internal.h"
+
+namespace f5 {
+
+int attn_plan(AttnPlan* pl, const void* qkv, void* out, int batches, int seq, int heads, const int* kv_len,
+              float scale) {
+  if (batches <= 0 || seq <= 0 || heads <= 0) {
+    set_error("attention: empty problem");
+    return -1;
+  }
+  const int inner = heads * 64;
+  int rc = encode_tmap_f16(&pl->tm, qkv, (uint64_t)3 * inner, (uint64_t)seq, (uint64_t)batches, (uint64_t)3 * inner * 2,
+                           (uint64_t)seq * 3 * inner * 2, 64, 128, 3);
+  if (rc) return rc;
+  pl->p.seq = seq;
+  pl->p.heads = heads;
+  pl->p.batches = batches;
+  pl->p.inner = inner;
+  pl->p.kv_len = kv_len;
+  pl->p.scale_log2 = scale * 1.4426950408889634f;
+  pl->p.out = reinterpret_cast<__half*>(out);
+  pl->grid = dim3((seq + kAttnBQ - 1) / kAttnBQ, heads, batches);
+  return 0;
+}
+
+int attn_configure() {
+  if (int rc = check_cuda(cudaFuncSetAttribute(attn_fwd_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               (int)kAttnSmem),
+                          "cudaFuncSetAttribute(attn smem)"))
+    return rc;
+  cudaFuncSetAttribute(attn_fwd_tcgen05_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  return 0;
+}
+
+int attn_run(const AttnPlan& pl, cudaStream_t s) {
+  if (int rc = configure_kernels()) return rc;
+  attn_fwd_tcgen05_kernel<<<pl.grid, kAttnThreads, kAttnSmem, s>>>(pl.tm, pl.p);
+  count_launch();
+  return check_launch("attn_fwd_tcgen05_kernel launch");
+}
+
+}  // namespace f5
+
+extern "C" int f5_attention(const void* qkv, void* out, int batches, int seq, int heads, const int* kv_len, float scale,
+                            f5_stream_t stream) {
+  f5::AttnPlan pl;
+  if (int rc = f5::attn_plan(&pl, qkv, out, batches, seq, heads, kv_len, scale)) return rc;
+  return f5::attn_run(pl, reinterpret_cast<cudaStream_t>(stream));
+}

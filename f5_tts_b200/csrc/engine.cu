@@ -1,0 +1,630 @@
+// Engine: the CFM.sample NFE loop (model/cfm.py:160-223) over a DiT (backbones/dit.py:319-370) or UNetT
+// (backbones/unett.py:244-307) backbone, expressed as a fixed kernel schedule over a caller-owned workspace.
+//
+// Per sample() call (hoisted out of the NFE loop because it is step- or batch-invariant):
+//   * text embeddings, cond + uncond variants (dit.py:284-314 caches them the same way)
+//   * time embedding of every grid point and — DiT — the AdaLN modulation vectors of every (step, block)
+//     as one [steps, depth*6D + 2D] table: 22 weight-streaming GEMVs per step become one GEMM per call
+//   * rotary cos/sin table, static columns of the packed input projection operand
+// Per NFE step: input projection -> grouped conv position embedding x2 (tensor-core implicit GEMM) -> depth x
+// {norm+modulate, fused QKV+RoPE GEMM, flash attention, out-proj (+gate, +mask, +residual), norm+modulate,
+//  FF1+GELU, FF2 (+gate, +residual)} -> final norm -> proj_out -> fused CFG + Euler update.
+// Every kernel reads the step index from a device counter, so one captured CUDA graph serves all steps.
+#include <cmath>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "internal.h"
+
+namespace f5 {
+
+static inline size_t al256(size_t x) { return (x + 255) & ~size_t(255); }
+
+struct Bump {
+  uint8_t* base;
+  size_t off = 0;
+  explicit Bump(void* p) : base(reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 255) & ~uintptr_t(255))) {}
+  template <typename T>
+  T* take(size_t count) {
+    T* r = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += al256(count * sizeof(T));
+    return r;
+  }
+};
+
+struct Layout {
+  // sizes
+  int B, Be, N, seq, steps, packed;
+  long long M, M1;
+  // common
+  int* step_ptr;
+  float* dt;
+  float* t_dev;
+  float *rope_cos, *rope_sin;
+  int* row_len;     // [Be] or unused
+  int* kv_len;      // [Be] or unused
+  int* valid_len;   // [B]
+  float *tfeat, *th1, *temb;
+  __half* temb_silu;
+  float* mod;
+  // text
+  float* tx;
+  uint8_t* filler;
+  __half *ta, *tg;
+  float *sumsq, *nx;
+  // step buffers
+  __half* xin;
+  float* h0;
+  __half *h0h, *c1;
+  float* x;                  // UNetT residual [M1, D]; DiT: alias of h0
+  std::vector<float*> skips;
+  __half* cat;
+  __half *a, *qkv, *ao, *g;
+  float* v;
+  size_t bytes;
+};
+
+}  // namespace f5
+
+using namespace f5;
+
+struct GraphEntry {
+  const void* ws;
+  f5_sample_args key;
+  cudaGraphExec_t exec;
+  int nodes;  // kernel/memcpy nodes per replay (for the launch counter)
+};
+
+struct f5_engine {
+  f5_arch arch;
+  f5_weights w;
+  std::vector<f5_layer_weights> layers;
+  int inner, modW, kin;
+  std::mutex mu;
+  std::vector<GraphEntry> graphs;
+};
+
+static void plan_layout(const f5_engine* e, Layout& L, void* ws, int B, int N, int steps, float cfg) {
+  const f5_arch& A = e->arch;
+  Bump bp(ws);
+  L.B = B;
+  L.N = N;
+  L.steps = steps;
+  L.packed = cfg < 1e-5f ? 0 : 1;
+  L.Be = L.packed ? 2 * B : B;
+  L.seq = A.backbone == 1 ? N + 1 : N;
+  L.M = (long long)L.Be * N;
+  L.M1 = (long long)L.Be * L.seq;
+  const int D = A.dim, Td = A.text_dim, F = A.ff_inner;
+  L.step_ptr = bp.take<int>(64);
+  L.dt = bp.take<float>(steps + 1);
+  L.t_dev = bp.take<float>(steps + 1);
+  L.rope_cos = bp.take<float>((size_t)L.seq * 32);
+  L.rope_sin = bp.take<float>((size_t)L.seq * 32);
+  L.row_len = bp.take<int>(L.Be);
+  L.kv_len = bp.take<int>(L.Be);
+  L.valid_len = bp.take<int>(B);
+  L.tfeat = bp.take<float>((size_t)steps * 256);
+  L.th1 = bp.take<float>((size_t)steps * D);
+  L.temb = bp.take<float>((size_t)steps * D);
+  L.temb_silu = bp.take<__half>((size_t)steps * D);
+  L.mod = bp.take<float>((size_t)steps * (e->modW > 0 ? e->modW : 1));
+  L.tx = bp.take<float>((size_t)2 * B * N * Td);
+  L.filler = bp.take<uint8_t>((size_t)B * N);
+  L.ta = bp.take<__half>((size_t)2 * B * N * Td);
+  L.tg = bp.take<__half>((size_t)2 * B * N * 2 * Td);
+  L.sumsq = bp.take<float>((size_t)2 * B * ((N + kGrnRows - 1) / kGrnRows) * 2 * Td);
+  L.nx = bp.take<float>((size_t)2 * B * 2 * Td);
+  L.xin = bp.take<__half>((size_t)L.M * e->kin);
+  L.h0 = bp.take<float>((size_t)L.M * D);
+  L.h0h = bp.take<__half>((size_t)L.M * D);
+  L.c1 = bp.take<__half>((size_t)L.M * D);
+  L.skips.clear();
+  if (A.backbone == 1) {
+    L.x = bp.take<float>((size_t)L.M1 * D);
+    for (int i = 0; i < A.depth / 2; ++i) L.skips.push_back(bp.take<float>((size_t)L.M1 * D));
+    L.cat = bp.take<__half>((size_t)L.M1 * 2 * D);
+  } else {
+    L.x = L.h0;
+    L.cat = nullptr;
+  }
+  L.a = bp.take<__half>((size_t)L.M1 * D);
+  L.qkv = bp.take<__half>((size_t)L.M1 * 3 * e->inner);
+  L.ao = bp.take<__half>((size_t)L.M1 * e->inner);
+  L.g = bp.take<__half>((size_t)L.M1 * F);
+  L.v = bp.take<float>((size_t)L.M1 * A.mel_dim);
+  L.bytes = bp.off + 512;
+}
+
+extern "C" {
+
+int f5_engine_create(const f5_arch* arch, const f5_weights* weights, f5_engine** out) {
+  if (!arch || !weights || !out) {
+    set_error("engine_create: null argument");
+    return -1;
+  }
+  if (arch->dim_head != 64) {
+    set_error("engine_create: dim_head must be 64 (got %d)", arch->dim_head);
+    return -1;
+  }
+  if (arch->dim % 128 || arch->dim > 1024 || (arch->ff_inner % 64)) {
+    set_error("engine_create: dim must be a multiple of 128 and <= 1024, ff_inner a multiple of 64 (dim=%d ff=%d)",
+              arch->dim, arch->ff_inner);
+    return -1;
+  }
+  if (arch->dim / 16 != 64) {
+    set_error("engine_create: ConvPositionEmbedding(groups=16) is built for 64 channels per group, i.e. dim == 1024");
+    return -1;
+  }
+  if (arch->conv_layers > 8 || (arch->conv_layers > 0 && (arch->text_dim % 64 || arch->text_dim > 512))) {
+    set_error("engine_create: text conv blocks need text_dim %% 64 == 0, <= 512, at most 8 layers");
+    return -1;
+  }
+  if (int rc = configure_kernels()) return rc;
+  f5_engine* e = new f5_engine();
+  e->arch = *arch;
+  e->w = *weights;
+  e->layers.assign(weights->layers, weights->layers + arch->depth);
+  e->w.layers = e->layers.data();
+  e->inner = arch->heads * arch->dim_head;
+  e->modW = arch->backbone == 0 ? arch->depth * 6 * arch->dim + 2 * arch->dim : 0;
+  e->kin = weights->proj_kpad;
+  if (e->kin % 64 || e->kin < 2 * arch->mel_dim + arch->text_dim) {
+    set_error("engine_create: proj_kpad must be a multiple of 64 covering 2*mel + text_dim");
+    delete e;
+    return -1;
+  }
+  *out = e;
+  return 0;
+}
+
+void f5_engine_destroy(f5_engine* e) {
+  if (!e) return;
+  for (auto& g : e->graphs) cudaGraphExecDestroy(g.exec);
+  delete e;
+}
+
+size_t f5_sample_workspace_bytes(const f5_engine* e, int B, int N, int steps, float cfg_strength) {
+  Layout L;
+  plan_layout(e, L, nullptr, B, N, steps, cfg_strength);
+  return L.bytes;
+}
+
+double f5_sample_flops(const f5_engine* e, int B, int N, int steps, float cfg_strength) {
+  const f5_arch& A = e->arch;
+  const double D = A.dim, mel = A.mel_dim, Td = A.text_dim, F = A.ff_inner, Ld = A.depth;
+  const double Be = cfg_strength < 1e-5f ? B : 2.0 * B;
+  double per;  // one sample-forward
+  if (A.backbone == 0) {
+    const double n = N;
+    per = Ld * (8.0 * n * D * D + 4.0 * n * D * F + 4.0 * n * n * D) + 2.0 * n * (2 * mel + Td) * D +
+          2.0 * (2.0 * n * D * (D / 16.0) * 31.0) + 2.0 * n * D * mel;
+  } else {
+    const double n1 = N + 1.0, n = N;
+    per = Ld * (8.0 * n1 * D * D + 4.0 * n1 * D * F + 4.0 * n1 * n1 * D) + (Ld / 2.0) * 4.0 * n1 * D * D +
+          2.0 * n * (2 * mel + Td) * D + 2.0 * (2.0 * n * D * (D / 16.0) * 31.0) + 2.0 * n1 * D * mel;
+  }
+  double total = steps * Be * per;
+  // text embedding, once per sample and CFG branch: conv_layers x (2 pointwise GEMMs)
+  total += 2.0 * B * A.conv_layers * (2.0 * 2.0 * N * Td * 2.0 * Td);
+  // conditioning: time MLP + AdaLN table, once per call
+  total += steps * (2.0 * 256 * D + 2.0 * D * D + 2.0 * D * (double)e->modW);
+  return total;
+}
+
+}  // extern "C"
+
+// -------------------------------------------------------------------------------------------------------------
+namespace {
+
+struct StepPlans {
+  GemmPlan proj, conv1, conv2, out_proj;
+  std::vector<GemmPlan> qkv, oproj, ff1, ff2, skip;
+  std::vector<AttnPlan> attn;  // identical per layer, kept once
+};
+
+#define RC(x)                \
+  do {                       \
+    int _rc = (x);           \
+    if (_rc) return _rc;     \
+  } while (0)
+
+f5_gemm_args base_args(long long rows, int n_out, int k, int lda, int ldw, int bn, int epi, int act) {
+  f5_gemm_args a{};
+  a.rows = (int)rows;
+  a.batches = 1;
+  a.n_out = n_out;
+  a.k = k;
+  a.lda = lda;
+  a.ldw = ldw;
+  a.bn = bn;
+  a.epi = epi;
+  a.act = act;
+  return a;
+}
+
+// tile-width heuristic: fill >= ~1.5 waves of 148 SMs when the problem is small, else use the widest tile
+int pick_bn(long long rows, int n_out, bool allow256) {
+  const long long mt = (rows + 127) / 128;
+  if (allow256 && mt * ((n_out + 255) / 256) >= 2 * 148) return 256;
+  if (mt * ((n_out + 127) / 128) >= 148 + 74) return 128;
+  return n_out % 64 == 0 ? 64 : 128;
+}
+
+int build_step_plans(f5_engine* e, const Layout& L, const f5_sample_args* sa, StepPlans& P) {
+  const f5_arch& A = e->arch;
+  const f5_weights& W = e->w;
+  const int D = A.dim, F = A.ff_inner, inner = e->inner;
+  const bool dit = A.backbone == 0;
+  const bool masked = sa->duration != nullptr;
+  const int pe_heads = A.pe_attn_head < 0 ? A.heads : A.pe_attn_head;
+  const long long modS = e->modW;
+
+  {  // input projection: h0 = xin . proj_w^T + b ; h0h = fp16(mask(h0))
+    f5_gemm_args a = base_args(L.M, D, e->kin, e->kin, e->kin, pick_bn(L.M, D, false), F5_EPI_F32, F5_ACT_NONE);
+    a.bias = W.proj_b;
+    a.out = L.h0;
+    a.out16b = L.h0h;
+    a.ldo = D;
+    a.seq = L.N;
+    a.row_len = (dit && masked) ? L.row_len : nullptr;
+    RC(gemm_plan(&P.proj, L.xin, W.proj_w, &a));
+  }
+  for (int c = 0; c < 2; ++c) {  // grouped conv position embedding
+    f5_gemm_args a{};
+    a.rows = L.N;
+    a.batches = L.Be;
+    a.n_out = D;
+    a.lda = D;
+    a.conv_taps = 31;
+    a.act = F5_ACT_MISH;
+    a.bias = W.conv_b[c];
+    a.ldo = D;
+    a.seq = L.N;
+    a.row_len = (dit && masked) ? L.row_len : nullptr;
+    if (c == 0) {
+      a.epi = F5_EPI_F16;
+      a.out = L.c1;
+      RC(gemm_plan(&P.conv1, L.h0h, W.conv_w[0], &a));
+    } else {
+      a.epi = F5_EPI_RESID;
+      a.resid = L.h0;
+      RC(gemm_plan(&P.conv2, L.c1, W.conv_w[1], &a));
+    }
+  }
+  P.qkv.resize(A.depth);
+  P.oproj.resize(A.depth);
+  P.ff1.resize(A.depth);
+  P.ff2.resize(A.depth);
+  P.skip.resize(A.depth);
+  const int* rl = masked ? L.row_len : nullptr;
+  for (int i = 0; i < A.depth; ++i) {
+    const f5_layer_weights& lw = W.layers[i];
+    if (!dit && lw.w_skip) {
+      f5_gemm_args a = base_args(L.M1, D, 2 * D, 2 * D, 2 * D, pick_bn(L.M1, D, false), F5_EPI_F32, F5_ACT_NONE);
+      a.out = L.x;
+      a.ldo = D;
+      RC(gemm_plan(&P.skip[i], L.cat, lw.w_skip, &a));
+    }
+    {
+      f5_gemm_args a = base_args(L.M1, 3 * inner, D, D, D, pick_bn(L.M1, 3 * inner, true), F5_EPI_QKV_ROPE, F5_ACT_NONE);
+      if (a.bn == 64) a.bn = 128;
+      a.bias = lw.b_qkv;
+      a.out = L.qkv;
+      a.ldo = 3 * inner;
+      a.seq = L.seq;
+      a.rope_cos = L.rope_cos;
+      a.rope_sin = L.rope_sin;
+      a.inner = inner;
+      a.pe_heads = pe_heads;
+      RC(gemm_plan(&P.qkv[i], L.a, lw.w_qkv, &a));
+    }
+    {
+      f5_gemm_args a = base_args(L.M1, D, inner, inner, inner, pick_bn(L.M1, D, false), F5_EPI_RESID, F5_ACT_NONE);
+      a.bias = lw.b_out;
+      a.resid = L.x;
+      a.ldo = D;
+      a.seq = L.seq;
+      a.row_len = rl;
+      if (dit) {
+        a.gate = L.mod + (size_t)i * 6 * D + 2 * D;
+        a.step_ptr = L.step_ptr;
+        a.gate_step_stride = modS;
+      }
+      RC(gemm_plan(&P.oproj[i], L.ao, lw.w_out, &a));
+    }
+    {
+      f5_gemm_args a = base_args(L.M1, F, D, D, D, pick_bn(L.M1, F, true), F5_EPI_F16, F5_ACT_GELU_TANH);
+      a.bias = lw.b_ff1;
+      a.out = L.g;
+      a.ldo = F;
+      RC(gemm_plan(&P.ff1[i], L.a, lw.w_ff1, &a));
+    }
+    {
+      f5_gemm_args a = base_args(L.M1, D, F, F, F, pick_bn(L.M1, D, false), F5_EPI_RESID, F5_ACT_NONE);
+      a.bias = lw.b_ff2;
+      a.resid = L.x;
+      a.ldo = D;
+      if (dit) {
+        a.gate = L.mod + (size_t)i * 6 * D + 5 * D;
+        a.step_ptr = L.step_ptr;
+        a.gate_step_stride = modS;
+      }
+      RC(gemm_plan(&P.ff2[i], L.g, lw.w_ff2, &a));
+    }
+  }
+  {
+    f5_gemm_args a = base_args(L.M1, A.mel_dim, D, D, D, 128, F5_EPI_F32, F5_ACT_NONE);
+    a.bias = W.out_b;
+    a.out = L.v;
+    a.ldo = A.mel_dim;
+    RC(gemm_plan(&P.out_proj, L.a, W.out_w, &a));
+  }
+  P.attn.resize(1);
+  RC(attn_plan(&P.attn[0], L.qkv, L.ao, L.Be, L.seq, A.heads, (A.attn_mask_enabled && masked) ? L.kv_len : nullptr,
+               1.0f / sqrtf((float)A.dim_head)));
+  return 0;
+}
+
+int norm_mod(const f5_engine* e, const Layout& L, const float* x, long long rows, int mode, const float* a,
+             const float* b, bool step_indexed, cudaStream_t s) {
+  NormParams p{};
+  p.x = x;
+  p.out = L.a;
+  p.rows = (int)rows;
+  p.D = e->arch.dim;
+  p.eps = 1e-6f;
+  p.a = a;
+  p.b = b;
+  p.step_ptr = step_indexed ? L.step_ptr : nullptr;
+  p.step_stride = step_indexed ? e->modW : 0;
+  return run_row_norm(mode, p, s);
+}
+
+int run_step(f5_engine* e, const Layout& L, const f5_sample_args* sa, const StepPlans& P, cudaStream_t s) {
+  const f5_arch& A = e->arch;
+  const int D = A.dim;
+  const bool dit = A.backbone == 0;
+  RC(gemm_run(P.proj, s));
+  RC(gemm_run(P.conv1, s));
+  RC(gemm_run(P.conv2, s));
+  if (!dit) RC(run_prepend_time_token(L.x, L.h0, L.temb, L.step_ptr, L.N, D, L.M1, s));
+  const int half = A.depth / 2;
+  for (int i = 0; i < A.depth; ++i) {
+    const f5_layer_weights& lw = e->w.layers[i];
+    if (dit) {
+      const float* m = L.mod + (size_t)i * 6 * D;
+      RC(norm_mod(e, L, L.x, L.M1, 0, m + D, m, true, s));  // scale_msa, shift_msa
+    } else {
+      if (i < half) {
+        RC(check_cuda(cudaMemcpyAsync(L.skips[i], L.x, sizeof(float) * L.M1 * D, cudaMemcpyDeviceToDevice, s),
+                      "skip copy"));
+      } else {
+        RC(run_concat_half(L.x, L.skips[A.depth - 1 - i], L.cat, L.M1, D, s));
+        RC(gemm_run(P.skip[i], s));
+      }
+      RC(norm_mod(e, L, L.x, L.M1, 2, lw.g_attn, nullptr, false, s));
+    }
+    RC(gemm_run(P.qkv[i], s));
+    RC(attn_run(P.attn[0], s));
+    RC(gemm_run(P.oproj[i], s));
+    if (dit) {
+      const float* m = L.mod + (size_t)i * 6 * D;
+      RC(norm_mod(e, L, L.x, L.M1, 0, m + 4 * D, m + 3 * D, true, s));  // scale_mlp, shift_mlp
+    } else {
+      RC(norm_mod(e, L, L.x, L.M1, 2, lw.g_ff, nullptr, false, s));
+    }
+    RC(gemm_run(P.ff1[i], s));
+    RC(gemm_run(P.ff2[i], s));
+  }
+  if (dit) {
+    const float* m = L.mod + (size_t)A.depth * 6 * D;
+    RC(norm_mod(e, L, L.x, L.M1, 0, m, m + D, true, s));  // AdaLayerNorm_Final: scale, shift (modules.py:342-347)
+  } else {
+    RC(norm_mod(e, L, L.x, L.M1, 2, e->w.g_out, nullptr, false, s));
+  }
+  RC(gemm_run(P.out_proj, s));
+  EulerParams ep{};
+  ep.y = sa->y;
+  ep.v = L.v;
+  ep.traj = sa->trajectory;
+  ep.xin = L.xin;
+  ep.dt = L.dt;
+  ep.step_ptr = L.step_ptr;
+  ep.BN = L.B * L.N;
+  ep.mel = A.mel_dim;
+  ep.Kpad = e->kin;
+  ep.packed = L.packed;
+  ep.N = L.N;
+  ep.seq_tok = L.seq;
+  ep.tok_off = dit ? 0 : 1;
+  ep.B = L.B;
+  ep.cfg = sa->cfg_strength;
+  return run_cfg_euler(ep, s);
+}
+
+int run_prologue(f5_engine* e, const Layout& L, const f5_sample_args* sa, cudaStream_t s) {
+  const f5_arch& A = e->arch;
+  const f5_weights& W = e->w;
+  const int D = A.dim, Td = A.text_dim, B = L.B, N = L.N, S = L.steps;
+  const bool dit = A.backbone == 0;
+  const bool masked = sa->duration != nullptr;
+  // small host -> device control data (pageable source: cudaMemcpyAsync stages it before returning)
+  std::vector<float> dt(S + 1, 0.f);
+  for (int k = 0; k < S; ++k) dt[k] = sa->t[k + 1] - sa->t[k];
+  RC(check_cuda(cudaMemcpyAsync(L.dt, dt.data(), sizeof(float) * (S + 1), cudaMemcpyHostToDevice, s), "dt h2d"));
+  RC(check_cuda(cudaMemcpyAsync(L.t_dev, sa->t, sizeof(float) * (S + 1), cudaMemcpyHostToDevice, s), "t h2d"));
+  RC(check_cuda(cudaMemsetAsync(L.step_ptr, 0, sizeof(int) * 64, s), "step memset"));
+  if (masked) {
+    // row_len[Be] = duration (+1 for the UNetT time token, unett.py:274-275); kv_len likewise
+    std::vector<int> hd(B);
+    RC(check_cuda(cudaMemcpyAsync(hd.data(), sa->duration, sizeof(int) * B, cudaMemcpyDeviceToHost, s), "dur d2h"));
+    RC(check_cuda(cudaStreamSynchronize(s), "dur sync"));
+    std::vector<int> rl(L.Be);
+    for (int i = 0; i < L.Be; ++i) rl[i] = hd[i % B] + (dit ? 0 : 1);
+    RC(check_cuda(cudaMemcpyAsync(L.row_len, rl.data(), sizeof(int) * L.Be, cudaMemcpyHostToDevice, s), "row_len"));
+    RC(check_cuda(cudaMemcpyAsync(L.kv_len, rl.data(), sizeof(int) * L.Be, cudaMemcpyHostToDevice, s), "kv_len"));
+    RC(check_cuda(cudaMemcpyAsync(L.valid_len, hd.data(), sizeof(int) * B, cudaMemcpyHostToDevice, s), "valid_len"));
+    RC(check_cuda(cudaStreamSynchronize(s), "len sync"));
+  }
+  RC(run_rope_table(L.rope_cos, L.rope_sin, L.seq, 32, s));
+  // time embedding for every grid point (modules.py:852-862)
+  RC(run_time_features(L.t_dev, L.tfeat, S, 256, s));
+  RC(run_small_linear(1, L.tfeat, reinterpret_cast<const __half*>(W.time_w0), W.time_b0, L.th1, S, 256, D, s));
+  RC(run_small_linear(0, L.th1, reinterpret_cast<const __half*>(W.time_w1), W.time_b1, L.temb, S, D, D, s));
+  if (dit) {
+    RC(run_silu_to_half(L.temb, L.temb_silu, (long long)S * D, s));
+    f5_gemm_args a = base_args(S, e->modW, D, D, D, 128, F5_EPI_F32, F5_ACT_NONE);
+    a.bias = W.mod_b;
+    a.out = L.mod;
+    a.ldo = e->modW;
+    GemmPlan pl;
+    RC(gemm_plan(&pl, L.temb_silu, W.mod_w, &a));
+    RC(gemm_run(pl, s));
+  }
+  // text embedding, both CFG variants (dit.py:86-139 / unett.py:55-84)
+  TextGatherParams tp{};
+  tp.ids = sa->text;
+  tp.B = B;
+  tp.nt = sa->nt;
+  tp.N = N;
+  tp.Td = Td;
+  tp.valid_len = (dit && masked) ? L.valid_len : nullptr;
+  tp.table = W.text_table;
+  tp.add_pos = A.conv_layers > 0;
+  tp.out = L.tx;
+  tp.filler = L.filler;
+  RC(run_text_gather(tp, s));
+  const int R2 = 2 * B * N;
+  for (int i = 0; i < A.conv_layers; ++i) {
+    if (A.text_mask_padding) RC(run_mask_rows(L.tx, L.filler, B * N, R2, Td, s));
+    DwConvLnParams dp{};
+    dp.x = L.tx;
+    dp.out = L.ta;
+    dp.B = 2 * B;
+    dp.N = N;
+    dp.C = Td;
+    dp.w = W.text_blocks[i].dw_w;
+    dp.wb = W.text_blocks[i].dw_b;
+    dp.ln_w = W.text_blocks[i].ln_w;
+    dp.ln_b = W.text_blocks[i].ln_b;
+    dp.eps = 1e-6f;
+    RC(run_dwconv7_ln(dp, s));
+    f5_gemm_args g1 = base_args(R2, 2 * Td, Td, Td, Td, 128, F5_EPI_F16, F5_ACT_GELU_ERF);
+    g1.bias = W.text_blocks[i].pw1_b;
+    g1.out = L.tg;
+    g1.ldo = 2 * Td;
+    RC(f5_gemm(L.ta, W.text_blocks[i].pw1_w, &g1, s));
+    RC(run_grn(L.tg, L.sumsq, L.nx, W.text_blocks[i].grn_gamma, W.text_blocks[i].grn_beta, 2 * B, N, 2 * Td, s));
+    f5_gemm_args g2 = base_args(R2, Td, 2 * Td, 2 * Td, 2 * Td, 64, F5_EPI_RESID, F5_ACT_NONE);
+    g2.bias = W.text_blocks[i].pw2_b;
+    g2.resid = L.tx;
+    g2.ldo = Td;
+    RC(f5_gemm(L.tg, W.text_blocks[i].pw2_w, &g2, s));
+  }
+  if (A.conv_layers > 0 && A.text_mask_padding) RC(run_mask_rows(L.tx, L.filler, B * N, R2, Td, s));
+  PackParams pp{};
+  pp.xin = L.xin;
+  pp.B = B;
+  pp.N = N;
+  pp.mel = A.mel_dim;
+  pp.Td = Td;
+  pp.Kpad = e->kin;
+  pp.packed = L.packed;
+  pp.y = sa->y;
+  pp.step_cond = sa->step_cond;
+  pp.text = L.tx;
+  RC(run_pack_input(pp, s));
+  if (sa->trajectory)
+    RC(check_cuda(cudaMemcpyAsync(sa->trajectory, sa->y, sizeof(float) * B * N * A.mel_dim, cudaMemcpyDeviceToDevice, s),
+                  "trajectory[0]"));
+  return 0;
+}
+
+int copy_v_out(const f5_engine* e, const Layout& L, const f5_sample_args* sa, cudaStream_t s) {
+  if (!sa->v_out) return 0;
+  const int mel = e->arch.mel_dim;
+  const int off = e->arch.backbone == 0 ? 0 : 1;
+  for (int b = 0; b < L.Be; ++b)
+    RC(check_cuda(cudaMemcpyAsync(sa->v_out + (size_t)b * L.N * mel, L.v + ((size_t)b * L.seq + off) * mel,
+                                  sizeof(float) * L.N * mel, cudaMemcpyDeviceToDevice, s),
+                  "v_out copy"));
+  return 0;
+}
+
+bool same_key(const f5_sample_args& a, const f5_sample_args& b) {
+  return a.B == b.B && a.N == b.N && a.nt == b.nt && a.steps == b.steps && a.text == b.text &&
+         a.step_cond == b.step_cond && a.y == b.y && a.duration == b.duration && a.trajectory == b.trajectory &&
+         (a.cfg_strength < 1e-5f) == (b.cfg_strength < 1e-5f) && a.cfg_strength == b.cfg_strength;
+}
+
+}  // namespace
+
+extern "C" int f5_sample(f5_engine* e, const f5_sample_args* sa, void* workspace, size_t ws_bytes, f5_stream_t stream) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (!e || !sa || !workspace) {
+    set_error("f5_sample: null argument");
+    return -1;
+  }
+  if (sa->B <= 0 || sa->N <= 0 || sa->steps <= 0 || sa->nt <= 0) {
+    set_error("f5_sample: empty problem (B=%d N=%d steps=%d nt=%d)", sa->B, sa->N, sa->steps, sa->nt);
+    return -1;
+  }
+  Layout L;
+  plan_layout(e, L, workspace, sa->B, sa->N, sa->steps, sa->cfg_strength);
+  if (ws_bytes < L.bytes) {
+    set_error("f5_sample: workspace too small (%zu < %zu)", ws_bytes, L.bytes);
+    return -1;
+  }
+  RC(run_prologue(e, L, sa, s));
+  cudaGraphExec_t exec = nullptr;
+  int nodes = 0;
+  if (sa->use_graph) {
+    std::lock_guard<std::mutex> lk(e->mu);
+    for (auto& g : e->graphs)
+      if (g.ws == workspace && same_key(g.key, *sa)) {
+        exec = g.exec;
+        nodes = g.nodes;
+      }
+    if (!exec) {
+      StepPlans P;
+      RC(build_step_plans(e, L, sa, P));
+      cudaGraph_t graph;
+      // capture on a private stream (the caller's stream may be the legacy default stream, which cannot capture);
+      // the instantiated graph is then launched into the caller's stream.
+      cudaStream_t cs;
+      RC(check_cuda(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking), "capture stream"));
+      if (int brc = check_cuda(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal), "begin capture")) {
+        cudaStreamDestroy(cs);
+        return brc;
+      }
+      const unsigned long long before = f5_launch_count();
+      int rc = run_step(e, L, sa, P, cs);
+      cudaError_t ce = cudaStreamEndCapture(cs, &graph);
+      cudaStreamDestroy(cs);
+      count_launch(-(int)(f5_launch_count() - before));  // captured, not launched
+      if (rc) return rc;
+      RC(check_cuda(ce, "end capture"));
+      size_t nn = 0;
+      cudaGraphGetNodes(graph, nullptr, &nn);
+      nodes = (int)nn;
+      RC(check_cuda(cudaGraphInstantiate(&exec, graph, 0), "graph instantiate"));
+      cudaGraphDestroy(graph);
+      if (e->graphs.size() >= 8) {
+        cudaGraphExecDestroy(e->graphs.front().exec);
+        e->graphs.erase(e->graphs.begin());
+      }
+      e->graphs.push_back(GraphEntry{workspace, *sa, exec, nodes});
+    }
+    for (int k = 0; k < sa->steps; ++k) {
+      RC(check_cuda(cudaGraphLaunch(exec, s), "graph launch"));
+    }
+    count_launch(nodes * sa->steps);
+    return copy_v_out(e, L, sa, s);
+  }
+  StepPlans P;
+  RC(build_step_plans(e, L, sa, P));
+  for (int k = 0; k < sa->steps; ++k) RC(run_step(e, L, sa, P, s));
+  return copy_v_out(e, L, sa, s);
+}

@@ -1,0 +1,230 @@
+// Host side of the tcgen05 GEMM: tensor-map encoding, instantiation table, launch, C entry point f5_gemm.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <atomic>
+
+#include "gemm.cuh"
+#include "internal.h"
+
+namespace f5 {
+
+static thread_local char g_err[512] = "";
+static std::atomic<unsigned long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add((unsigned long long)(long long)n, std::memory_order_relaxed); }
+int check_cuda(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return 0;
+  set_error("%s: %s", what, cudaGetErrorString(e));
+  return -2;
+}
+int check_launch(const char* what) { return check_cuda(cudaGetLastError(), what); }
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+int encode_tmap_f16(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1,
+                    uint64_t stride2, uint32_t b0, uint32_t b1, int rank) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver / not a TMA-capable device)");
+    return -3;
+  }
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (stride1 & 15) || (rank == 3 && (stride2 & 15))) {
+    set_error("tensor map: pointer/strides must be 16-byte aligned (ptr=%p s1=%llu s2=%llu)", ptr,
+              (unsigned long long)stride1, (unsigned long long)stride2);
+    return -4;
+  }
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {stride1, stride2};
+  cuuint32_t box[3] = {b0, b1, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides, box,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed: %d (dims %llu,%llu,%llu box %u,%u)", (int)r, (unsigned long long)d0,
+              (unsigned long long)d1, (unsigned long long)d2, b0, b1);
+    return -5;
+  }
+  return 0;
+}
+
+int configure_kernels();
+
+template <int BN, int STAGES, int EPI, int ACT, bool CONV>
+static int launch_inst(const GemmPlan& pl, cudaStream_t s) {
+  auto kern = gemm_tcgen05_kernel<BN, STAGES, EPI, ACT, CONV>;
+  constexpr size_t smem = gemm_smem_bytes<BN, STAGES>();
+  if (int rc = configure_kernels()) return rc;
+  kern<<<pl.grid, kGemmThreads, smem, s>>>(pl.tmA, pl.tmB, pl.p);
+  count_launch();
+  return check_launch("gemm_tcgen05_kernel launch");
+}
+
+template <int BN, int STAGES, int EPI, int ACT, bool CONV>
+static int configure_inst() {
+  auto kern = gemm_tcgen05_kernel<BN, STAGES, EPI, ACT, CONV>;
+  constexpr size_t smem = gemm_smem_bytes<BN, STAGES>();
+  if (int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                          "cudaFuncSetAttribute(gemm smem)"))
+    return rc;
+  cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  return 0;
+}
+
+#define F5_GEMM_CASE(BN_, ST_, EPI_, ACT_, CONV_)                                          \
+  if (pl.bn == BN_ && pl.epi == EPI_ && pl.act == ACT_ && (pl.conv != 0) == CONV_)        \
+    return launch_inst<BN_, ST_, EPI_, ACT_, CONV_>(pl, s);
+
+int configure_kernels() {
+  static std::atomic<int> done{0};
+  if (done.load()) return 0;
+    if (int rc = configure_inst<64, 4, EPI_F16, ACT_NONE, false>()) return rc;
+    if (int rc = configure_inst<128, 3, EPI_F16, ACT_NONE, false>()) return rc;
+    if (int rc = configure_inst<256, 4, EPI_F16, ACT_NONE, false>()) return rc;
+    if (int rc = configure_inst<64, 4, EPI_F16, ACT_GELU_TANH, false>()) return rc;
+    if (int rc = configure_inst<128, 3, EPI_F16, ACT_GELU_TANH, false>()) return rc;
+    if (int rc = configure_inst<256, 4, EPI_F16, ACT_GELU_TANH, false>()) return rc;
+    if (int rc = configure_inst<64, 4, EPI_F16, ACT_GELU_ERF, false>()) return rc;
+    if (int rc = configure_inst<128, 3, EPI_F16, ACT_GELU_ERF, false>()) return rc;
+    if (int rc = configure_inst<64, 4, EPI_F32, ACT_NONE, false>()) return rc;
+    if (int rc = configure_inst<128, 3, EPI_F32, ACT_NONE, false>()) return rc;
+    if (int rc = configure_inst<64, 4, EPI_RESID, ACT_NONE, false>()) return rc;
+    if (int rc = configure_inst<128, 3, EPI_RESID, ACT_NONE, false>()) return rc;
+    if (int rc = configure_inst<128, 3, EPI_QKV_ROPE, ACT_NONE, false>()) return rc;
+    if (int rc = configure_inst<256, 4, EPI_QKV_ROPE, ACT_NONE, false>()) return rc;
+    if (int rc = configure_inst<64, 4, EPI_F16, ACT_MISH, true>()) return rc;
+    if (int rc = configure_inst<64, 4, EPI_RESID, ACT_MISH, true>()) return rc;
+  if (int rc = attn_configure()) return rc;
+  done.store(1);
+  return 0;
+}
+
+int gemm_run(const GemmPlan& pl, cudaStream_t s) {
+  F5_GEMM_CASE(64, 4, EPI_F16, ACT_NONE, false)
+  F5_GEMM_CASE(128, 3, EPI_F16, ACT_NONE, false)
+  F5_GEMM_CASE(256, 4, EPI_F16, ACT_NONE, false)
+  F5_GEMM_CASE(64, 4, EPI_F16, ACT_GELU_TANH, false)
+  F5_GEMM_CASE(128, 3, EPI_F16, ACT_GELU_TANH, false)
+  F5_GEMM_CASE(256, 4, EPI_F16, ACT_GELU_TANH, false)
+  F5_GEMM_CASE(64, 4, EPI_F16, ACT_GELU_ERF, false)
+  F5_GEMM_CASE(128, 3, EPI_F16, ACT_GELU_ERF, false)
+  F5_GEMM_CASE(64, 4, EPI_F32, ACT_NONE, false)
+  F5_GEMM_CASE(128, 3, EPI_F32, ACT_NONE, false)
+  F5_GEMM_CASE(64, 4, EPI_RESID, ACT_NONE, false)
+  F5_GEMM_CASE(128, 3, EPI_RESID, ACT_NONE, false)
+  F5_GEMM_CASE(128, 3, EPI_QKV_ROPE, ACT_NONE, false)
+  F5_GEMM_CASE(256, 4, EPI_QKV_ROPE, ACT_NONE, false)
+  F5_GEMM_CASE(64, 4, EPI_F16, ACT_MISH, true)
+  F5_GEMM_CASE(64, 4, EPI_RESID, ACT_MISH, true)
+  set_error("gemm: no kernel instantiated for bn=%d epi=%d act=%d conv=%d", pl.bn, pl.epi, pl.act, pl.conv);
+  return -6;
+}
+
+int gemm_plan(GemmPlan* pl, const void* A, const void* W, const f5_gemm_args* a) {
+  memset(pl, 0, sizeof(*pl));
+  const bool conv = a->conv_taps > 0;
+  int bn = a->bn;
+  if (conv) bn = 64;
+  if (bn == 0) bn = 128;
+  if (bn != 64 && bn != 128 && bn != 256) {
+    set_error("gemm: bn must be 64, 128 or 256");
+    return -1;
+  }
+  if (a->rows <= 0 || a->batches <= 0 || a->n_out <= 0) {
+    set_error("gemm: empty problem (rows=%d batches=%d n_out=%d)", a->rows, a->batches, a->n_out);
+    return -1;
+  }
+  if (a->epi == F5_EPI_QKV_ROPE && (a->inner % 64 || a->rope_cos == nullptr || a->seq <= 0)) {
+    set_error("gemm: QKV_ROPE needs inner %% 64 == 0, rope tables and seq");
+    return -1;
+  }
+  pl->bn = bn;
+  pl->epi = a->epi;
+  pl->act = a->act;
+  pl->conv = conv ? 1 : 0;
+  GemmParams& p = pl->p;
+  p.rows = a->rows;
+  p.n_out = a->n_out;
+  p.batches = a->batches;
+  p.bias = a->bias;
+  p.out = a->out;
+  p.out16b = reinterpret_cast<__half*>(a->out16b);
+  p.resid = a->resid;
+  p.ldo = a->ldo;
+  p.gate = a->gate;
+  p.step_ptr = a->step_ptr;
+  p.gate_step_stride = a->gate_step_stride;
+  p.row_len = a->row_len;
+  p.seq = a->seq;
+  p.rope_cos = a->rope_cos;
+  p.rope_sin = a->rope_sin;
+  p.inner = a->inner > 0 ? a->inner : 64;
+  p.pe_heads = a->pe_heads;
+  p.conv_pad = a->conv_taps / 2;
+  int rc;
+  if (conv) {
+    if (a->n_out % 64 || a->lda < a->n_out) {
+      set_error("conv gemm: channels must be a multiple of 64 (got %d, lda %d)", a->n_out, a->lda);
+      return -1;
+    }
+    p.num_kb = a->conv_taps;
+    // activations [batches][rows][lda]: channel slice of 64 = one group
+    rc = encode_tmap_f16(&pl->tmA, A, (uint64_t)a->lda, (uint64_t)a->rows, (uint64_t)a->batches, (uint64_t)a->lda * 2,
+                         (uint64_t)a->rows * a->lda * 2, 64, 128, 3);
+    if (rc) return rc;
+    rc = encode_tmap_f16(&pl->tmB, W, 64, (uint64_t)a->conv_taps * a->n_out, 1, 128, 0, 64, 64, 2);
+    if (rc) return rc;
+  } else {
+    if (a->k <= 0 || a->lda < a->k || a->ldw < a->k) {
+      set_error("gemm: bad k/lda/ldw (%d, %d, %d)", a->k, a->lda, a->ldw);
+      return -1;
+    }
+    p.num_kb = (a->k + kBK - 1) / kBK;
+    rc = encode_tmap_f16(&pl->tmA, A, (uint64_t)a->k, (uint64_t)a->rows, (uint64_t)a->batches, (uint64_t)a->lda * 2,
+                         (uint64_t)a->rows * a->lda * 2, 64, 128, 3);
+    if (rc) return rc;
+    rc = encode_tmap_f16(&pl->tmB, W, (uint64_t)a->k, (uint64_t)a->n_out, 1, (uint64_t)a->ldw * 2, 0, 64, (uint32_t)bn, 2);
+    if (rc) return rc;
+  }
+  pl->grid = dim3((a->n_out + bn - 1) / bn, (a->rows + kBM - 1) / kBM, a->batches);
+  return 0;
+}
+
+}  // namespace f5
+
+extern "C" {
+
+int f5_version(void) { return 100; }
+const char* f5_last_error(void) { return f5::g_err; }
+unsigned long long f5_launch_count(void) { return f5::g_launches.load(); }
+
+int f5_gemm(const void* A, const void* W, const f5_gemm_args* args, f5_stream_t stream) {
+  f5::GemmPlan pl;
+  if (int rc = f5::gemm_plan(&pl, A, W, args)) return rc;
+  return f5::gemm_run(pl, reinterpret_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,62 @@
+// Internal host-side declarations shared by the translation units of libf5tts_b200.so.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include "../../include/f5tts_b200.h"
+#include "kparams.h"
+
+namespace f5 {
+
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+int check_cuda(cudaError_t e, const char* what);
+int check_launch(const char* what);
+int configure_kernels();  // cudaFuncSetAttribute for every instantiation (once per process)
+int attn_configure();
+
+struct GemmPlan {
+  CUtensorMap tmA, tmB;
+  GemmParams p;
+  dim3 grid;
+  int bn, epi, act, conv;
+};
+int gemm_plan(GemmPlan* plan, const void* A, const void* W, const f5_gemm_args* a);
+int gemm_run(const GemmPlan& plan, cudaStream_t s);
+
+struct AttnPlan {
+  CUtensorMap tm;
+  AttnParams p;
+  dim3 grid;
+};
+int attn_plan(AttnPlan* plan, const void* qkv, void* out, int batches, int seq, int heads, const int* kv_len,
+              float scale);
+int attn_run(const AttnPlan& plan, cudaStream_t s);
+
+// 3-D fp16 tensor map: dims (d0 contiguous, d1, d2), byte strides for d1, d2, box (b0, b1, 1), 128B swizzle
+int encode_tmap_f16(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1,
+                    uint64_t stride2, uint32_t b0, uint32_t b1, int rank);
+
+}  // namespace f5
+
+// ---- launch wrappers of the bandwidth-bound kernels (defined in ops.cu) ----
+#include "ew_params.h"
+namespace f5 {
+int run_row_norm(int mode, const NormParams& p, cudaStream_t s);
+int run_dwconv7_ln(const DwConvLnParams& p, cudaStream_t s);
+int run_text_gather(const TextGatherParams& p, cudaStream_t s);
+int run_mask_rows(float* x, const uint8_t* filler, int BN, int rows, int C, cudaStream_t s);
+constexpr int kGrnRows = 64;  // sequence rows per partial-sum block
+int run_grn(__half* g, float* partial, float* nx, const float* gamma, const float* beta, int B, int N, int C,
+            cudaStream_t s);
+int run_pack_input(const PackParams& p, cudaStream_t s);
+int run_cfg_euler(const EulerParams& p, cudaStream_t s);
+int run_small_linear(int act, const float* in, const __half* W, const float* bias, float* out, int S, int K, int Nout,
+                     cudaStream_t s);
+int run_time_features(const float* t, float* feat, int S, int dim, cudaStream_t s);
+int run_silu_to_half(const float* in, __half* out, long long n, cudaStream_t s);
+int run_rope_table(float* cs, float* sn, int seq, int half, cudaStream_t s);
+int run_prepend_time_token(float* dst, const float* src, const float* t_emb, const int* step_ptr, int N, int D,
+                           long long rows_out, cudaStream_t s);
+int run_concat_half(const float* x, const float* skip, __half* out, long long rows, int D, cudaStream_t s);
+}  // namespace f5

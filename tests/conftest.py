@@ -18,3 +18,18 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
+
+
+@pytest.fixture(autouse=True)
+def _gpu_test_deadline(request):
+    """Hard per-test deadline for GPU tests: a wedged kernel must not eat the GPU lease."""
+    if request.node.get_closest_marker("gpu") is None:
+        yield
+        return
+    import faulthandler
+
+    faulthandler.dump_traceback_later(240, exit=True)
+    try:
+        yield
+    finally:
+        faulthandler.cancel_dump_traceback_later()
