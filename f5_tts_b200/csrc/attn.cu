@@ -21,7 +21,7 @@ int attn_plan(AttnPlan* pl, const void* qkv, void* out, int batches, int seq, in
   pl->p.kv_len = kv_len;
   pl->p.scale_log2 = scale * 1.4426950408889634f;
   pl->p.out = reinterpret_cast<__half*>(out);
-  pl->grid = dim3((seq + kAttnBQ - 1) / kAttnBQ, heads, batches);
+  pl->grid = dim3((seq + 2 * kAttnBQ - 1) / (2 * kAttnBQ), heads, batches);
   return 0;
 }
 

@@ -244,12 +244,25 @@ f5_gemm_args base_args(long long rows, int n_out, int k, int lda, int ldw, int b
   return a;
 }
 
-// tile-width heuristic: fill >= ~1.5 waves of 148 SMs when the problem is small, else use the widest tile
+// Tile-width heuristic for the persistent GEMM: with one CTA per SM the kernel time is
+// rounds x k-blocks x per-k-block cost, and the per-k-block cost is dominated by the L2 -> SM operand stream
+// ((128 + BN) x 64 fp16 per k-block), so minimise rounds x (128 + BN); ties go to the wider tile (less total traffic).
 int pick_bn(long long rows, int n_out, bool allow256) {
   const long long mt = (rows + 127) / 128;
-  if (allow256 && mt * ((n_out + 255) / 256) >= 2 * 148) return 256;
-  if (mt * ((n_out + 127) / 128) >= 148 + 74) return 128;
-  return n_out % 64 == 0 ? 64 : 128;
+  const int sms = num_sms();
+  int best = 128;
+  long long best_cost = -1;
+  for (int bn : {64, 128, 256}) {
+    if (bn == 256 && !allow256) continue;
+    if (bn == 64 && n_out % 64) continue;
+    const long long tiles = mt * ((n_out + bn - 1) / bn);
+    const long long cost = ((tiles + sms - 1) / sms) * (128 + bn);
+    if (best_cost < 0 || cost < best_cost || (cost == best_cost && bn > best)) {
+      best = bn;
+      best_cost = cost;
+    }
+  }
+  return best;
 }
 
 int build_step_plans(f5_engine* e, const Layout& L, const f5_sample_args* sa, StepPlans& P) {
@@ -262,7 +275,7 @@ int build_step_plans(f5_engine* e, const Layout& L, const f5_sample_args* sa, St
   const long long modS = e->modW;
 
   {  // input projection: h0 = xin . proj_w^T + b ; h0h = fp16(mask(h0))
-    f5_gemm_args a = base_args(L.M, D, e->kin, e->kin, e->kin, pick_bn(L.M, D, false), F5_EPI_F32, F5_ACT_NONE);
+    f5_gemm_args a = base_args(L.M, D, e->kin, e->kin, e->kin, pick_bn(L.M, D, true), F5_EPI_F32, F5_ACT_NONE);
     a.bias = W.proj_b;
     a.out = L.h0;
     a.out16b = L.h0h;
@@ -302,7 +315,7 @@ int build_step_plans(f5_engine* e, const Layout& L, const f5_sample_args* sa, St
   for (int i = 0; i < A.depth; ++i) {
     const f5_layer_weights& lw = W.layers[i];
     if (!dit && lw.w_skip) {
-      f5_gemm_args a = base_args(L.M1, D, 2 * D, 2 * D, 2 * D, pick_bn(L.M1, D, false), F5_EPI_F32, F5_ACT_NONE);
+      f5_gemm_args a = base_args(L.M1, D, 2 * D, 2 * D, 2 * D, pick_bn(L.M1, D, true), F5_EPI_F32, F5_ACT_NONE);
       a.out = L.x;
       a.ldo = D;
       RC(gemm_plan(&P.skip[i], L.cat, lw.w_skip, &a));
@@ -321,7 +334,7 @@ int build_step_plans(f5_engine* e, const Layout& L, const f5_sample_args* sa, St
       RC(gemm_plan(&P.qkv[i], L.a, lw.w_qkv, &a));
     }
     {
-      f5_gemm_args a = base_args(L.M1, D, inner, inner, inner, pick_bn(L.M1, D, false), F5_EPI_RESID, F5_ACT_NONE);
+      f5_gemm_args a = base_args(L.M1, D, inner, inner, inner, pick_bn(L.M1, D, true), F5_EPI_RESID, F5_ACT_NONE);
       a.bias = lw.b_out;
       a.resid = L.x;
       a.ldo = D;
@@ -342,7 +355,7 @@ int build_step_plans(f5_engine* e, const Layout& L, const f5_sample_args* sa, St
       RC(gemm_plan(&P.ff1[i], L.a, lw.w_ff1, &a));
     }
     {
-      f5_gemm_args a = base_args(L.M1, D, F, F, F, pick_bn(L.M1, D, false), F5_EPI_RESID, F5_ACT_NONE);
+      f5_gemm_args a = base_args(L.M1, D, F, F, F, pick_bn(L.M1, D, true), F5_EPI_RESID, F5_ACT_NONE);
       a.bias = lw.b_ff2;
       a.resid = L.x;
       a.ldo = D;

@@ -2,6 +2,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <atomic>
 
 #include "gemm.cuh"
@@ -10,6 +11,7 @@
 namespace f5 {
 
 static thread_local char g_err[512] = "";
+static long long* g_trace = nullptr;
 static std::atomic<unsigned long long> g_launches{0};
 
 void set_error(const char* fmt, ...) {
@@ -46,6 +48,11 @@ static EncodeTiledFn get_encode_fn() {
 
 int encode_tmap_f16(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1,
                     uint64_t stride2, uint32_t b0, uint32_t b1, int rank) {
+  return encode_tmap(m, 0, ptr, d0, d1, d2, stride1, stride2, b0, b1, rank);
+}
+
+int encode_tmap(CUtensorMap* m, int is_f32, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1,
+                uint64_t stride2, uint32_t b0, uint32_t b1, int rank) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver / not a TMA-capable device)");
@@ -60,7 +67,7 @@ int encode_tmap_f16(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, u
   cuuint64_t strides[2] = {stride1, stride2};
   cuuint32_t box[3] = {b0, b1, 1};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides, box,
+  CUresult r = fn(m, is_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides, box,
                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -72,13 +79,14 @@ int encode_tmap_f16(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, u
 }
 
 int configure_kernels();
+int num_sms();
 
 template <int BN, int STAGES, int EPI, int ACT, bool CONV>
 static int launch_inst(const GemmPlan& pl, cudaStream_t s) {
   auto kern = gemm_tcgen05_kernel<BN, STAGES, EPI, ACT, CONV>;
   constexpr size_t smem = gemm_smem_bytes<BN, STAGES>();
   if (int rc = configure_kernels()) return rc;
-  kern<<<pl.grid, kGemmThreads, smem, s>>>(pl.tmA, pl.tmB, pl.p);
+  kern<<<pl.grid, kGemmThreads, smem, s>>>(pl.tmA, pl.tmB, pl.tmC, pl.p);
   count_launch();
   return check_launch("gemm_tcgen05_kernel launch");
 }
@@ -101,44 +109,60 @@ static int configure_inst() {
 int configure_kernels() {
   static std::atomic<int> done{0};
   if (done.load()) return 0;
-    if (int rc = configure_inst<64, 4, EPI_F16, ACT_NONE, false>()) return rc;
-    if (int rc = configure_inst<128, 3, EPI_F16, ACT_NONE, false>()) return rc;
-    if (int rc = configure_inst<256, 4, EPI_F16, ACT_NONE, false>()) return rc;
-    if (int rc = configure_inst<64, 4, EPI_F16, ACT_GELU_TANH, false>()) return rc;
-    if (int rc = configure_inst<128, 3, EPI_F16, ACT_GELU_TANH, false>()) return rc;
-    if (int rc = configure_inst<256, 4, EPI_F16, ACT_GELU_TANH, false>()) return rc;
-    if (int rc = configure_inst<64, 4, EPI_F16, ACT_GELU_ERF, false>()) return rc;
-    if (int rc = configure_inst<128, 3, EPI_F16, ACT_GELU_ERF, false>()) return rc;
-    if (int rc = configure_inst<64, 4, EPI_F32, ACT_NONE, false>()) return rc;
-    if (int rc = configure_inst<128, 3, EPI_F32, ACT_NONE, false>()) return rc;
-    if (int rc = configure_inst<64, 4, EPI_RESID, ACT_NONE, false>()) return rc;
-    if (int rc = configure_inst<128, 3, EPI_RESID, ACT_NONE, false>()) return rc;
-    if (int rc = configure_inst<128, 3, EPI_QKV_ROPE, ACT_NONE, false>()) return rc;
-    if (int rc = configure_inst<256, 4, EPI_QKV_ROPE, ACT_NONE, false>()) return rc;
-    if (int rc = configure_inst<64, 4, EPI_F16, ACT_MISH, true>()) return rc;
-    if (int rc = configure_inst<64, 4, EPI_RESID, ACT_MISH, true>()) return rc;
+  if (int rc = configure_inst<64, 8, EPI_F16, ACT_NONE, false>()) return rc;
+  if (int rc = configure_inst<64, 8, EPI_F16, ACT_GELU_TANH, false>()) return rc;
+  if (int rc = configure_inst<64, 8, EPI_F16, ACT_GELU_ERF, false>()) return rc;
+  if (int rc = configure_inst<64, 8, EPI_F32, ACT_NONE, false>()) return rc;
+  if (int rc = configure_inst<64, 8, EPI_RESID, ACT_NONE, false>()) return rc;
+  if (int rc = configure_inst<128, 6, EPI_F16, ACT_NONE, false>()) return rc;
+  if (int rc = configure_inst<128, 6, EPI_F16, ACT_GELU_TANH, false>()) return rc;
+  if (int rc = configure_inst<128, 6, EPI_F16, ACT_GELU_ERF, false>()) return rc;
+  if (int rc = configure_inst<128, 6, EPI_F32, ACT_NONE, false>()) return rc;
+  if (int rc = configure_inst<128, 6, EPI_RESID, ACT_NONE, false>()) return rc;
+  if (int rc = configure_inst<256, 4, EPI_F16, ACT_NONE, false>()) return rc;
+  if (int rc = configure_inst<256, 4, EPI_F16, ACT_GELU_TANH, false>()) return rc;
+  if (int rc = configure_inst<256, 4, EPI_F16, ACT_GELU_ERF, false>()) return rc;
+  if (int rc = configure_inst<256, 4, EPI_F32, ACT_NONE, false>()) return rc;
+  if (int rc = configure_inst<256, 4, EPI_RESID, ACT_NONE, false>()) return rc;
+  if (int rc = configure_inst<128, 6, EPI_QKV_ROPE, ACT_NONE, false>()) return rc;
+  if (int rc = configure_inst<256, 4, EPI_QKV_ROPE, ACT_NONE, false>()) return rc;
+  if (int rc = configure_inst<64, 8, EPI_F16, ACT_MISH, true>()) return rc;
+  if (int rc = configure_inst<64, 8, EPI_RESID, ACT_MISH, true>()) return rc;
   if (int rc = attn_configure()) return rc;
   done.store(1);
   return 0;
 }
 
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
 int gemm_run(const GemmPlan& pl, cudaStream_t s) {
-  F5_GEMM_CASE(64, 4, EPI_F16, ACT_NONE, false)
-  F5_GEMM_CASE(128, 3, EPI_F16, ACT_NONE, false)
+  F5_GEMM_CASE(64, 8, EPI_F16, ACT_NONE, false)
+  F5_GEMM_CASE(64, 8, EPI_F16, ACT_GELU_TANH, false)
+  F5_GEMM_CASE(64, 8, EPI_F16, ACT_GELU_ERF, false)
+  F5_GEMM_CASE(64, 8, EPI_F32, ACT_NONE, false)
+  F5_GEMM_CASE(64, 8, EPI_RESID, ACT_NONE, false)
+  F5_GEMM_CASE(128, 6, EPI_F16, ACT_NONE, false)
+  F5_GEMM_CASE(128, 6, EPI_F16, ACT_GELU_TANH, false)
+  F5_GEMM_CASE(128, 6, EPI_F16, ACT_GELU_ERF, false)
+  F5_GEMM_CASE(128, 6, EPI_F32, ACT_NONE, false)
+  F5_GEMM_CASE(128, 6, EPI_RESID, ACT_NONE, false)
   F5_GEMM_CASE(256, 4, EPI_F16, ACT_NONE, false)
-  F5_GEMM_CASE(64, 4, EPI_F16, ACT_GELU_TANH, false)
-  F5_GEMM_CASE(128, 3, EPI_F16, ACT_GELU_TANH, false)
   F5_GEMM_CASE(256, 4, EPI_F16, ACT_GELU_TANH, false)
-  F5_GEMM_CASE(64, 4, EPI_F16, ACT_GELU_ERF, false)
-  F5_GEMM_CASE(128, 3, EPI_F16, ACT_GELU_ERF, false)
-  F5_GEMM_CASE(64, 4, EPI_F32, ACT_NONE, false)
-  F5_GEMM_CASE(128, 3, EPI_F32, ACT_NONE, false)
-  F5_GEMM_CASE(64, 4, EPI_RESID, ACT_NONE, false)
-  F5_GEMM_CASE(128, 3, EPI_RESID, ACT_NONE, false)
-  F5_GEMM_CASE(128, 3, EPI_QKV_ROPE, ACT_NONE, false)
+  F5_GEMM_CASE(256, 4, EPI_F16, ACT_GELU_ERF, false)
+  F5_GEMM_CASE(256, 4, EPI_F32, ACT_NONE, false)
+  F5_GEMM_CASE(256, 4, EPI_RESID, ACT_NONE, false)
+  F5_GEMM_CASE(128, 6, EPI_QKV_ROPE, ACT_NONE, false)
   F5_GEMM_CASE(256, 4, EPI_QKV_ROPE, ACT_NONE, false)
-  F5_GEMM_CASE(64, 4, EPI_F16, ACT_MISH, true)
-  F5_GEMM_CASE(64, 4, EPI_RESID, ACT_MISH, true)
+  F5_GEMM_CASE(64, 8, EPI_F16, ACT_MISH, true)
+  F5_GEMM_CASE(64, 8, EPI_RESID, ACT_MISH, true)
   set_error("gemm: no kernel instantiated for bn=%d epi=%d act=%d conv=%d", pl.bn, pl.epi, pl.act, pl.conv);
   return -6;
 }
@@ -184,6 +208,22 @@ int gemm_plan(GemmPlan* pl, const void* A, const void* W, const f5_gemm_args* a)
   p.inner = a->inner > 0 ? a->inner : 64;
   p.pe_heads = a->pe_heads;
   p.conv_pad = a->conv_taps / 2;
+  {
+    static int dbg = -1;
+    if (dbg < 0) {
+      const char* e = getenv("F5_GEMM_DBG");
+      dbg = e ? atoi(e) : 0;
+    }
+    p.dbg_mode = dbg;
+    static long long* trace = nullptr;
+    static int want_trace = -1;
+    if (want_trace < 0) {
+      want_trace = getenv("F5_GEMM_TRACE") ? 1 : 0;
+      if (want_trace) cudaMalloc(&trace, sizeof(long long) * 8 * 1024);
+    }
+    p.dbg_ts = trace;
+    g_trace = trace;
+  }
   int rc;
   if (conv) {
     if (a->n_out % 64 || a->lda < a->n_out) {
@@ -209,7 +249,28 @@ int gemm_plan(GemmPlan* pl, const void* A, const void* W, const f5_gemm_args* a)
     rc = encode_tmap_f16(&pl->tmB, W, (uint64_t)a->k, (uint64_t)a->n_out, 1, (uint64_t)a->ldw * 2, 0, 64, (uint32_t)bn, 2);
     if (rc) return rc;
   }
-  pl->grid = dim3((a->n_out + bn - 1) / bn, (a->rows + kBM - 1) / kBM, a->batches);
+  // output tensor map for the staged epilogues (bulk TMA store of fp16 / reduce-add of fp32); columns clip at n_out
+  if (a->epi == F5_EPI_F32) {
+    pl->tmC = pl->tmA;  // unused
+  } else if (a->epi == F5_EPI_RESID) {
+    if (a->ldo % 4 || a->resid == nullptr) {
+      set_error("gemm: RESID epilogue needs resid != NULL and ldo %% 4 == 0 (ldo=%d)", a->ldo);
+      return -1;
+    }
+    rc = encode_tmap(&pl->tmC, 1, a->resid, (uint64_t)a->n_out, (uint64_t)a->rows, (uint64_t)a->batches,
+                     (uint64_t)a->ldo * 4, (uint64_t)a->rows * a->ldo * 4, 32, 128, 3);
+    if (rc) return rc;
+  } else {
+    if (a->ldo % 8 || a->out == nullptr) {
+      set_error("gemm: fp16 epilogue needs out != NULL and ldo %% 8 == 0 (ldo=%d)", a->ldo);
+      return -1;
+    }
+    rc = encode_tmap(&pl->tmC, 0, a->out, (uint64_t)a->n_out, (uint64_t)a->rows, (uint64_t)a->batches,
+                     (uint64_t)a->ldo * 2, (uint64_t)a->rows * a->ldo * 2, 64, 128, 3);
+    if (rc) return rc;
+  }
+  const long long tiles = (long long)((a->n_out + bn - 1) / bn) * ((a->rows + kBM - 1) / kBM) * a->batches;
+  pl->grid = dim3((unsigned)(tiles < num_sms() ? tiles : num_sms()), 1, 1);  // persistent: one CTA per SM
   return 0;
 }
 
@@ -220,6 +281,13 @@ extern "C" {
 int f5_version(void) { return 100; }
 const char* f5_last_error(void) { return f5::g_err; }
 unsigned long long f5_launch_count(void) { return f5::g_launches.load(); }
+
+// diagnostics: copy the per-CTA timestamp trace of the last GEMM launched with F5_GEMM_TRACE=1 (8 values per CTA)
+int f5_debug_gemm_trace(long long* host_out, int n_ctas) {
+  if (!f5::g_trace) return -1;
+  cudaDeviceSynchronize();
+  return cudaMemcpy(host_out, f5::g_trace, sizeof(long long) * 8 * (size_t)n_ctas, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -2;
+}
 
 int f5_gemm(const void* A, const void* W, const f5_gemm_args* args, f5_stream_t stream) {
   f5::GemmPlan pl;

@@ -1,13 +1,19 @@
-// tcgen05 GEMM / grouped-conv-as-GEMM for sm_100a.
+// Persistent, warp-specialised tcgen05 GEMM / grouped-conv-as-GEMM for sm_100a.
 //
 //   C[m, n] = epilogue( sum_k A[m, k] * W[n, k] )        A, W fp16, K-major; fp32 accumulation in TMEM.
 //
-// One CTA per 128 x BN output tile.  Warp roles (192 threads): warp 0 = TMA producer (one elected lane),
-// warp 1 = TMEM allocator + single-thread tcgen05.mma issuer, warps 2..5 = epilogue (TMEM -> registers -> global),
-// each epilogue warp owning TMEM lane quarter (warp % 4).  Operand tiles are 64 fp16 wide (128 B rows) in
-// SWIZZLE_128B layout written by TMA and read through UMMA shared-memory descriptors; a STAGES-deep
-// full/empty mbarrier ring decouples TMA from the tensor core.  Tails in M, N and K are handled by TMA
-// out-of-bounds zero fill plus guarded stores.
+// grid = min(#tiles, #SMs); every CTA walks tiles t = blockIdx.x, +gridDim.x, ... (n fastest, so CTAs that run
+// together share the A row-panel in L2 and sweep W once).  Warp roles (192 threads):
+//   warp 0        TMA producer (one elected lane): STAGES-deep ring of {A 128x64, W BNx64} fp16 tiles, SWIZZLE_128B
+//   warp 1        TMEM allocator + single-thread tcgen05.mma issuer; accumulators double-buffered in TMEM
+//                 (2 x BN columns) so the epilogue of tile i overlaps the main loop of tile i+1
+//   warps 2..5    epilogue: tcgen05.ld (one accumulator row per thread) -> fused bias / activation / RoPE / gate /
+//                 mask -> 128-byte row chunks staged in shared memory (128B swizzle, conflict free) -> ONE elected
+//                 thread issues a bulk TMA store (fp16 outputs) or a TMA reduce-add (fp32 residual: x += ..., the
+//                 residual is never read by the SM).  Per-thread scattered global stores were measured 2.4x slower
+//                 than the whole main loop.  Warp w owns TMEM lane quarter (w % 4).
+// Pipelines: smem full/empty mbarriers (TMA <-> MMA), TMEM acc_full/acc_empty mbarriers (MMA <-> epilogue).
+// Tails in M, N and K come from TMA out-of-bounds zero fill plus guarded stores.
 //
 // CONV mode computes the reference's grouped Conv1d(k=31, groups=16, padding=15) (model/modules.py:175-201)
 // as 31 accumulated 128x64x64 GEMMs: tap t multiplies the activation tile shifted by (t - 15) rows — the shift is
@@ -19,18 +25,192 @@
 
 namespace f5 {
 
+constexpr uint32_t kEpiChunkBytes = kBM * 128;  // 128 rows x 128 B (64 fp16 or 32 fp32 columns)
+
 template <int BN, int STAGES>
 constexpr size_t gemm_smem_bytes() {
-  return size_t(STAGES) * (kBM * kBK * 2 + BN * kBK * 2) + 1024 /*align slack*/ + 256 /*barriers*/;
+  return size_t(STAGES) * (kBM * kBK * 2 + BN * kBK * 2) + 2 * kEpiChunkBytes /*epilogue staging*/ +
+         1024 /*align slack*/ + 256 /*barriers*/;
+}
+
+// Values of one 32-column chunk of one accumulator row after bias / RoPE / activation (no store).
+template <int EPI, int ACT>
+__device__ __forceinline__ void epilogue_values(const GemmParams& p, const uint32_t (&r)[32], int nc, int pos,
+                                                float (&v)[32]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.bias != nullptr) {
+      if (nc + 4 * i + 3 < p.n_out) b = __ldg(reinterpret_cast<const float4*>(p.bias + nc) + i);
+      else {
+        if (nc + 4 * i + 0 < p.n_out) b.x = __ldg(p.bias + nc + 4 * i + 0);
+        if (nc + 4 * i + 1 < p.n_out) b.y = __ldg(p.bias + nc + 4 * i + 1);
+        if (nc + 4 * i + 2 < p.n_out) b.z = __ldg(p.bias + nc + 4 * i + 2);
+      }
+    }
+    v[4 * i + 0] = __uint_as_float(r[4 * i + 0]) + b.x;
+    v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + b.y;
+    v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + b.z;
+    v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + b.w;
+  }
+  if (EPI == EPI_QKV_ROPE) {
+    const int sec = nc / p.inner;
+    const int head = (nc % p.inner) / 64;
+    if (sec < 2 && head < p.pe_heads) {
+      const int pair0 = (nc % 64) / 2;
+      const float4* cs = reinterpret_cast<const float4*>(p.rope_cos + (long long)pos * 32 + pair0);
+      const float4* sn = reinterpret_cast<const float4*>(p.rope_sin + (long long)pos * 32 + pair0);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 c4 = __ldg(cs + i), s4 = __ldg(sn + i);
+        const float cc[4] = {c4.x, c4.y, c4.z, c4.w}, ss[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float x0 = v[8 * i + 2 * j], x1 = v[8 * i + 2 * j + 1];
+          v[8 * i + 2 * j] = x0 * cc[j] - x1 * ss[j];
+          v[8 * i + 2 * j + 1] = x1 * cc[j] + x0 * ss[j];
+        }
+      }
+    }
+  }
+  if (ACT != ACT_NONE) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      if (ACT == ACT_GELU_TANH) v[i] = gelu_tanh(v[i]);
+      if (ACT == ACT_GELU_ERF) v[i] = gelu_erf(v[i]);
+      if (ACT == ACT_MISH) v[i] = mish(v[i]);
+    }
+  }
+}
+
+// fused epilogue for one 32-column chunk of one accumulator row
+template <int EPI, int ACT>
+__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32_t (&r)[32], int nc, long long grow,
+                                               int pos, bool valid, const float* gate) {
+  float v[32];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.bias != nullptr) {
+      if (nc + 4 * i + 3 < p.n_out) b = __ldg(reinterpret_cast<const float4*>(p.bias + nc) + i);
+      else {
+        if (nc + 4 * i + 0 < p.n_out) b.x = __ldg(p.bias + nc + 4 * i + 0);
+        if (nc + 4 * i + 1 < p.n_out) b.y = __ldg(p.bias + nc + 4 * i + 1);
+        if (nc + 4 * i + 2 < p.n_out) b.z = __ldg(p.bias + nc + 4 * i + 2);
+      }
+    }
+    v[4 * i + 0] = __uint_as_float(r[4 * i + 0]) + b.x;
+    v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + b.y;
+    v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + b.z;
+    v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + b.w;
+  }
+  if (EPI == EPI_QKV_ROPE) {
+    const int sec = nc / p.inner;
+    const int head = (nc % p.inner) / 64;
+    if (sec < 2 && head < p.pe_heads) {
+      const int pair0 = (nc % 64) / 2;
+      const float4* cs = reinterpret_cast<const float4*>(p.rope_cos + (long long)pos * 32 + pair0);
+      const float4* sn = reinterpret_cast<const float4*>(p.rope_sin + (long long)pos * 32 + pair0);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 c4 = __ldg(cs + i), s4 = __ldg(sn + i);
+        const float cc[4] = {c4.x, c4.y, c4.z, c4.w}, ss[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float x0 = v[8 * i + 2 * j], x1 = v[8 * i + 2 * j + 1];
+          v[8 * i + 2 * j] = x0 * cc[j] - x1 * ss[j];
+          v[8 * i + 2 * j + 1] = x1 * cc[j] + x0 * ss[j];
+        }
+      }
+    }
+  }
+  if (ACT != ACT_NONE) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      if (ACT == ACT_GELU_TANH) v[i] = gelu_tanh(v[i]);
+      if (ACT == ACT_GELU_ERF) v[i] = gelu_erf(v[i]);
+      if (ACT == ACT_MISH) v[i] = mish(v[i]);
+    }
+  }
+  const bool full_chunk = (nc + 32 <= p.n_out);
+  if (EPI == EPI_F16 || EPI == EPI_QKV_ROPE) {
+    __half* o = reinterpret_cast<__half*>(p.out) + grow * p.ldo + nc;
+    if (full_chunk && (p.ldo % 8 == 0)) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint4 w;
+        w.x = valid ? pack_half2(v[8 * i + 0], v[8 * i + 1]) : 0u;
+        w.y = valid ? pack_half2(v[8 * i + 2], v[8 * i + 3]) : 0u;
+        w.z = valid ? pack_half2(v[8 * i + 4], v[8 * i + 5]) : 0u;
+        w.w = valid ? pack_half2(v[8 * i + 6], v[8 * i + 7]) : 0u;
+        reinterpret_cast<uint4*>(o)[i] = w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)  // static indices only: a dynamic index would push v[] into local memory
+        if (nc + i < p.n_out) o[i] = __float2half_rn(valid ? v[i] : 0.0f);
+    }
+  } else if (EPI == EPI_F32) {
+    float* o = reinterpret_cast<float*>(p.out) + grow * p.ldo + nc;
+    if (full_chunk && (p.ldo % 4 == 0)) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        reinterpret_cast<float4*>(o)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (nc + i < p.n_out) o[i] = v[i];
+    }
+    if (p.out16b != nullptr) {
+      __half* o2 = p.out16b + grow * p.ldo + nc;
+      if (full_chunk && (p.ldo % 8 == 0)) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 w;
+          w.x = valid ? pack_half2(v[8 * i + 0], v[8 * i + 1]) : 0u;
+          w.y = valid ? pack_half2(v[8 * i + 2], v[8 * i + 3]) : 0u;
+          w.z = valid ? pack_half2(v[8 * i + 4], v[8 * i + 5]) : 0u;
+          w.w = valid ? pack_half2(v[8 * i + 6], v[8 * i + 7]) : 0u;
+          reinterpret_cast<uint4*>(o2)[i] = w;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; i += 2)
+          if (nc + i < p.n_out) *reinterpret_cast<uint32_t*>(o2 + i) = valid ? pack_half2(v[i], v[i + 1]) : 0u;
+      }
+    }
+  } else if (EPI == EPI_RESID) {
+    float* o = p.resid + grow * p.ldo + nc;
+    if (!valid) return;
+    if (full_chunk && (p.ldo % 4 == 0)) {
+      float4 x[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x[i] = reinterpret_cast<const float4*>(o)[i];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float4 g = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (gate != nullptr) g = __ldg(reinterpret_cast<const float4*>(gate + nc) + i);
+        x[i].x += g.x * v[4 * i];
+        x[i].y += g.y * v[4 * i + 1];
+        x[i].z += g.z * v[4 * i + 2];
+        x[i].w += g.w * v[4 * i + 3];
+        reinterpret_cast<float4*>(o)[i] = x[i];
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (nc + i < p.n_out) o[i] += (gate ? gate[nc + i] : 1.0f) * v[i];
+    }
+  }
 }
 
 template <int BN, int STAGES, int EPI, int ACT, bool CONV>
-__global__ void __launch_bounds__(kGemmThreads)
+__global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const GemmParams p) {
+                    const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
   constexpr uint32_t A_BYTES = kBM * kBK * 2;
   constexpr uint32_t B_BYTES = BN * kBK * 2;
-  constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+  constexpr uint32_t TMEM_COLS = 2 * BN;  // double-buffered accumulator (power of two: 128 / 256 / 512)
   static_assert(BN == 64 || BN == 128 || BN == 256, "BN");
 
   extern __shared__ uint8_t smem_raw[];
@@ -38,24 +218,37 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * A_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * (A_BYTES + B_BYTES));
+  uint8_t* sC = smem + STAGES * (A_BYTES + B_BYTES);  // 2 x 16 KB epilogue staging (1024-aligned)
+  uint64_t* full = reinterpret_cast<uint64_t*>(sC + 2 * kEpiChunkBytes);
   uint64_t* empty = full + STAGES;
-  uint64_t* acc_full = empty + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+  uint64_t* acc_full = empty + STAGES;  // [2]
+  uint64_t* acc_empty = acc_full + 2;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5;
-  const int n0 = blockIdx.x * BN;
-  const int m0 = blockIdx.y * kBM;
-  const int bz = blockIdx.z;
+  long long* ts = p.dbg_ts ? p.dbg_ts + (long long)blockIdx.x * 8 : nullptr;
+  if (ts && threadIdx.x == 0) {
+    unsigned long long g;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+    ts[0] = (long long)g;
+    ts[1] = clock64();
+  }
+  const int tiles_n = (p.n_out + BN - 1) / BN;
+  const int tiles_m = (p.rows + kBM - 1) / kBM;
+  const int num_tiles = tiles_n * tiles_m * p.batches;
 
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (EPI != EPI_F32) tma_prefetch_desc(&tmC);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
-    mbar_init(acc_full, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_empty[b], 128);
+    }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -63,23 +256,34 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (ts && threadIdx.x == 0) ts[2] = clock64();  // setup done
 
   if (warp == 0) {
     if (elect_one()) {
       // ===== TMA producer =====
-      for (int kb = 0; kb < p.num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(&empty[s], ph ^ 1);
-        mbar_expect_tx(&full[s], A_BYTES + B_BYTES);
-        if (CONV) {
-          // A: activation [batch][seq][channels]; group = blockIdx.x (BN == 64 == channels per group)
-          tma_load_3d(sA + s * A_BYTES, &tmA, &full[s], n0, m0 + kb - p.conv_pad, bz);
-          // W repacked [tap][out_channel][in 64]: rows = tap * n_out + out_channel
-          tma_load_2d(sB + s * B_BYTES, &tmB, &full[s], 0, kb * p.n_out + n0);
-        } else {
-          tma_load_3d(sA + s * A_BYTES, &tmA, &full[s], kb * kBK, m0, bz);
-          tma_load_2d(sB + s * B_BYTES, &tmB, &full[s], kb * kBK, n0);
+      uint32_t it = 0;  // running k-block counter across tiles -> stage / phase
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int n0 = (t % tiles_n) * BN;
+        const int m0 = ((t / tiles_n) % tiles_m) * kBM;
+        const int bz = t / (tiles_n * tiles_m);
+        for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          if (p.dbg_mode == 1) {
+            mbar_arrive(&full[s]);
+            continue;
+          }
+          mbar_expect_tx(&full[s], A_BYTES + B_BYTES);
+          if (CONV) {
+            // A: activation [batch][seq][channels]; group = n-tile (BN == 64 == channels per group)
+            tma_load_3d(sA + s * A_BYTES, &tmA, &full[s], n0, m0 + kb - p.conv_pad, bz);
+            // W repacked [tap][out_channel][in 64]: rows = tap * n_out + out_channel
+            tma_load_2d(sB + s * B_BYTES, &tmB, &full[s], 0, kb * p.n_out + n0);
+          } else {
+            tma_load_3d(sA + s * A_BYTES, &tmA, &full[s], kb * kBK, m0, bz);
+            tma_load_2d(sB + s * B_BYTES, &tmB, &full[s], kb * kBK, n0);
+          }
         }
       }
     }
@@ -87,135 +291,138 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (elect_one()) {
       // ===== MMA issuer =====
       constexpr uint32_t idesc = make_idesc_f16(kBM, BN, 0, 0);
-      for (int kb = 0; kb < p.num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(&full[s], ph);
+      uint32_t it = 0, tl = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++tl) {
+        const uint32_t buf = tl & 1;
+        mbar_wait(&acc_empty[buf], ((tl >> 1) & 1) ^ 1);  // epilogue drained this accumulator
         tc_fence_after();
-        const uint64_t adesc = make_smem_desc_sw128(smem_u32(sA + s * A_BYTES));
-        const uint64_t bdesc = make_smem_desc_sw128(smem_u32(sB + s * B_BYTES));
+        const uint32_t tmem_acc = tmem_base + buf * BN;
+        for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&full[s], ph);
+          if (ts && it == 0) ts[3] = clock64();  // first operands landed
+          tc_fence_after();
+          const uint64_t adesc = make_smem_desc_sw128(smem_u32(sA + s * A_BYTES));
+          const uint64_t bdesc = make_smem_desc_sw128(smem_u32(sB + s * B_BYTES));
 #pragma unroll
-        for (int k = 0; k < kBK / 16; ++k) {
-          // +32 bytes (16 fp16) along K inside the 128B swizzle atom = +2 in the (addr >> 4) field
-          tc_mma_ss(tmem_base, adesc + uint64_t(k * 2), bdesc + uint64_t(k * 2), idesc, (kb | k) != 0);
+          for (int k = 0; k < kBK / 16; ++k) {
+            if (p.dbg_mode == 2) break;
+            // +32 bytes (16 fp16) along K inside the 128B swizzle atom = +2 in the (addr >> 4) field
+            tc_mma_ss(tmem_acc, adesc + uint64_t(k * 2), bdesc + uint64_t(k * 2), idesc, (kb | k) != 0);
+          }
+          tc_commit(&empty[s]);  // smem slot reusable once these MMAs retire
         }
-        tc_commit(&empty[s]);  // smem slot reusable once these MMAs retire
+        tc_commit(&acc_full[buf]);
       }
-      tc_commit(acc_full);
+      if (ts) ts[4] = clock64();  // all MMAs issued
     }
   } else {
     // ===== epilogue: warps 2..5 -> TMEM lane quarters 2,3,0,1 =====
     const int q = warp & 3;
-    const int row_in_batch = m0 + q * 32 + int(lane_id());
-    const bool row_ok = row_in_batch < p.rows;
-    const long long grow = (long long)bz * p.rows + row_in_batch;
-    bool valid = row_ok;
-    int pos = 0;
-    if (p.seq > 0) {
-      pos = int(grow % p.seq);
-      if (p.row_len != nullptr && row_ok) valid = pos < p.row_len[grow / p.seq];
-    }
     const float* gate = nullptr;
-    if (EPI == EPI_RESID && p.gate != nullptr) gate = p.gate + (p.step_ptr ? (long long)(*p.step_ptr) : 0) * p.gate_step_stride;
-
-    mbar_wait(acc_full, 0);
-    tc_fence_after();
+    if (EPI == EPI_RESID && p.gate != nullptr)
+      gate = p.gate + (p.step_ptr ? (long long)(*p.step_ptr) : 0) * p.gate_step_stride;
+    uint32_t tl = 0, chunk_ctr = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++tl) {
+      const int n0 = (t % tiles_n) * BN;
+      const int m0 = ((t / tiles_n) % tiles_m) * kBM;
+      const int bz = t / (tiles_n * tiles_m);
+      const uint32_t buf = tl & 1;
+      const int row_in_batch = m0 + q * 32 + int(lane_id());
+      const bool row_ok = row_in_batch < p.rows;
+      const long long grow = (long long)bz * p.rows + row_in_batch;
+      bool valid = row_ok;
+      int pos = 0;
+      if (p.seq > 0) {
+        pos = int(grow % p.seq);
+        if (p.row_len != nullptr && row_ok) valid = pos < p.row_len[grow / p.seq];
+      }
+      mbar_wait(&acc_full[buf], (tl >> 1) & 1);
+      if (ts && tl == 0 && threadIdx.x == 64) ts[5] = clock64();  // first accumulator complete
+      tc_fence_after();
+      const uint32_t tmem_acc = tmem_base + buf * BN + (uint32_t(q * 32) << 16);
+      if (EPI == EPI_F32) {
+        // direct stores (used once per step for the input projection: fp32 + masked fp16 copy)
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      uint32_t r[32];
-      tmem_ld32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(c * 32), r);
-      tmem_ld_wait();
-      const int nc = n0 + c * 32;
-      if (!row_ok || nc >= p.n_out) continue;
-      float v[32];
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        float b = (p.bias != nullptr && nc + i < p.n_out) ? __ldg(p.bias + nc + i) : 0.0f;
-        v[i] = __uint_as_float(r[i]) + b;
-      }
-      if (EPI == EPI_QKV_ROPE) {
-        const int sec = nc / p.inner;
-        const int head = (nc % p.inner) / 64;
-        if (sec < 2 && head < p.pe_heads) {
-          const int pair0 = (nc % 64) / 2;
-          const float* cs = p.rope_cos + (long long)pos * 32 + pair0;
-          const float* sn = p.rope_sin + (long long)pos * 32 + pair0;
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float c_ = __ldg(cs + i), s_ = __ldg(sn + i);
-            const float x0 = v[2 * i], x1 = v[2 * i + 1];
-            v[2 * i] = x0 * c_ - x1 * s_;
-            v[2 * i + 1] = x1 * c_ + x0 * s_;
-          }
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld32(tmem_acc + uint32_t(c * 32), r);
+          tmem_ld_wait();
+          const int nc = n0 + c * 32;
+          if (row_ok && nc < p.n_out && p.dbg_mode != 3) epilogue_chunk<EPI, ACT>(p, r, nc, grow, pos, valid, gate);
         }
-      }
-      if (ACT != ACT_NONE) {
+      } else {
+        // staged: 128-byte row chunks -> swizzled smem -> bulk TMA store / reduce-add
+        constexpr int CH_COLS = (EPI == EPI_RESID) ? 32 : 64;
+        const int erow = q * 32 + int(lane_id());
+        const bool issuer = (threadIdx.x == 64);
+#pragma unroll 1
+        for (int ch = 0; ch < BN / CH_COLS; ++ch, ++chunk_ctr) {
+          uint8_t* sbuf = sC + (chunk_ctr & 1) * kEpiChunkBytes;
+          if (issuer) tma_store_wait_read<1>();  // the store that last used this buffer has drained it
+          named_bar_sync(1, 128);
+          uint8_t* srow = sbuf + erow * 128;
+          if (EPI == EPI_RESID) {
+            uint32_t r[32];
+            tmem_ld32(tmem_acc + uint32_t(ch * 32), r);
+            tmem_ld_wait();
+            const int nc = n0 + ch * 32;
+            float v[32];
+            epilogue_values<EPI, ACT>(p, r, nc, pos, v);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          if (ACT == ACT_GELU_TANH) v[i] = gelu_tanh(v[i]);
-          if (ACT == ACT_GELU_ERF) v[i] = gelu_erf(v[i]);
-          if (ACT == ACT_MISH) v[i] = mish(v[i]);
-        }
-      }
-      const bool full_chunk = (nc + 32 <= p.n_out);
-      if (EPI == EPI_F16 || EPI == EPI_QKV_ROPE) {
-        __half* o = reinterpret_cast<__half*>(p.out) + grow * p.ldo + nc;
-        if (full_chunk && (p.ldo % 8 == 0)) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            uint4 w;
-            w.x = valid ? pack_half2(v[8 * i + 0], v[8 * i + 1]) : 0u;
-            w.y = valid ? pack_half2(v[8 * i + 2], v[8 * i + 3]) : 0u;
-            w.z = valid ? pack_half2(v[8 * i + 4], v[8 * i + 5]) : 0u;
-            w.w = valid ? pack_half2(v[8 * i + 6], v[8 * i + 7]) : 0u;
-            reinterpret_cast<uint4*>(o)[i] = w;
-          }
-        } else {
-          for (int i = 0; i < 32 && nc + i < p.n_out; ++i) o[i] = __float2half_rn(valid ? v[i] : 0.0f);
-        }
-      } else if (EPI == EPI_F32) {
-        float* o = reinterpret_cast<float*>(p.out) + grow * p.ldo + nc;
-        if (full_chunk && (p.ldo % 4 == 0)) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            reinterpret_cast<float4*>(o)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-        } else {
-          for (int i = 0; i < 32 && nc + i < p.n_out; ++i) o[i] = v[i];
-        }
-        if (p.out16b != nullptr) {
-          __half* o2 = p.out16b + grow * p.ldo + nc;
-          for (int i = 0; i < 32 && nc + i < p.n_out; i += 2)
-            *reinterpret_cast<uint32_t*>(o2 + i) = valid ? pack_half2(v[i], v[i + 1]) : 0u;
-        }
-      } else if (EPI == EPI_RESID) {
-        float* o = p.resid + grow * p.ldo + nc;
-        if (full_chunk && (p.ldo % 4 == 0)) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            float4 x = reinterpret_cast<float4*>(o)[i];
-            float g0 = 1.f, g1 = 1.f, g2 = 1.f, g3 = 1.f;
-            if (gate != nullptr) {
-              const float4 g = __ldg(reinterpret_cast<const float4*>(gate + nc) + i);
-              g0 = g.x; g1 = g.y; g2 = g.z; g3 = g.w;
+            for (int i = 0; i < 8; ++i) {
+              float4 g = make_float4(1.f, 1.f, 1.f, 1.f);
+              if (gate != nullptr && nc + 4 * i + 3 < p.n_out) g = __ldg(reinterpret_cast<const float4*>(gate + nc) + i);
+              float4 o;
+              o.x = valid ? g.x * v[4 * i] : 0.f;
+              o.y = valid ? g.y * v[4 * i + 1] : 0.f;
+              o.z = valid ? g.z * v[4 * i + 2] : 0.f;
+              o.w = valid ? g.w * v[4 * i + 3] : 0.f;
+              *reinterpret_cast<float4*>(srow + ((i ^ (erow & 7)) << 4)) = o;
             }
-            if (valid) {
-              x.x += g0 * v[4 * i];
-              x.y += g1 * v[4 * i + 1];
-              x.z += g2 * v[4 * i + 2];
-              x.w += g3 * v[4 * i + 3];
-              reinterpret_cast<float4*>(o)[i] = x;
+          } else {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              uint32_t r[32];
+              tmem_ld32(tmem_acc + uint32_t(ch * 64 + h * 32), r);
+              tmem_ld_wait();
+              const int nc = n0 + ch * 64 + h * 32;
+              float v[32];
+              epilogue_values<EPI, ACT>(p, r, nc, pos, v);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                uint4 w;
+                w.x = valid ? pack_half2(v[8 * i + 0], v[8 * i + 1]) : 0u;
+                w.y = valid ? pack_half2(v[8 * i + 2], v[8 * i + 3]) : 0u;
+                w.z = valid ? pack_half2(v[8 * i + 4], v[8 * i + 5]) : 0u;
+                w.w = valid ? pack_half2(v[8 * i + 6], v[8 * i + 7]) : 0u;
+                *reinterpret_cast<uint4*>(srow + (((h * 4 + i) ^ (erow & 7)) << 4)) = w;
+              }
             }
           }
-        } else {
-          for (int i = 0; i < 32 && nc + i < p.n_out; ++i)
-            if (valid) o[i] += (gate ? gate[nc + i] : 1.0f) * v[i];
+          fence_proxy_async_smem();
+          named_bar_sync(2, 128);
+          if (issuer && p.dbg_mode != 3) {
+            const int c0 = n0 + ch * CH_COLS;
+            if (c0 < p.n_out) {
+              if (EPI == EPI_RESID) tma_reduce_add_3d(&tmC, sbuf, c0, m0, bz);
+              else tma_store_3d(&tmC, sbuf, c0, m0, bz);
+            }
+            tma_store_commit();
+          }
         }
       }
+      tc_fence_before();
+      mbar_arrive(&acc_empty[buf]);
     }
+    if (EPI != EPI_F32 && threadIdx.x == 64) tma_store_wait_all();  // smem must outlive the last bulk store
+    if (ts && threadIdx.x == 64) ts[6] = clock64();  // epilogue done
   }
 
   tc_fence_before();
   __syncthreads();
+  if (ts && threadIdx.x == 0) ts[7] = clock64();
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 

@@ -14,9 +14,10 @@ int check_cuda(cudaError_t e, const char* what);
 int check_launch(const char* what);
 int configure_kernels();  // cudaFuncSetAttribute for every instantiation (once per process)
 int attn_configure();
+int num_sms();
 
 struct GemmPlan {
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmC;
   GemmParams p;
   dim3 grid;
   int bn, epi, act, conv;
@@ -34,6 +35,8 @@ int attn_plan(AttnPlan* plan, const void* qkv, void* out, int batches, int seq, 
 int attn_run(const AttnPlan& plan, cudaStream_t s);
 
 // 3-D fp16 tensor map: dims (d0 contiguous, d1, d2), byte strides for d1, d2, box (b0, b1, 1), 128B swizzle
+int encode_tmap(CUtensorMap* m, int is_f32, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1,
+                uint64_t stride2, uint32_t b0, uint32_t b1, int rank);
 int encode_tmap_f16(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1,
                     uint64_t stride2, uint32_t b0, uint32_t b1, int rank);
 

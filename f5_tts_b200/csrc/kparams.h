@@ -34,6 +34,8 @@ struct GemmParams {
   int inner;     // heads * dim_head
   int pe_heads;  // heads that get rotary (q and k sections)
   int conv_pad;  // CONV: taps/2
+  long long* dbg_ts;  // optional [gridDim.x][8] clock64/globaltimer trace (diagnostics; NULL in production)
+  int dbg_mode;  // 0 normal; 1 = skip TMA loads, 2 = skip MMAs, 3 = skip epilogue math/stores (perf decomposition only)
 };
 
 constexpr int kGemmThreads = 192;
@@ -51,12 +53,12 @@ struct AttnParams {
   __half* out;        // [Be*seq, inner]
 };
 
-constexpr int kAttnThreads = 192;
-constexpr int kAttnBQ = 128;
+constexpr int kAttnThreads = 320;   // TMA warp + MMA warp + 2 softmax warpgroups
+constexpr int kAttnBQ = 128;        // rows per query tile (two tiles per CTA)
 constexpr int kAttnBKV = 128;
-constexpr int kAttnStages = 2;
-constexpr uint32_t kAttnTile = 128 * 64 * 2;                                        // 16 KB
-constexpr size_t kAttnSmem = kAttnTile * (1 + 2 * kAttnStages + 2) + 1024;          // Q + K,V stages + P(2 sub-tiles) + slack
-
+constexpr int kAttnStages = 3;      // K and V rings
+constexpr uint32_t kAttnTile = 128 * 64 * 2;  // 16 KB
+// Q x2 + K,V rings + P (2 warpgroups x 2 sub-tiles) + alignment slack + barriers
+constexpr size_t kAttnSmem = size_t(kAttnTile) * (2 + 2 * kAttnStages + 4) + 1024 + 256;
 
 }  // namespace f5
