@@ -133,7 +133,7 @@ def launch_count() -> int:
 
 
 EXPORTED_SYMBOLS = [
-    "f5_version", "f5_last_error", "f5_launch_count", "f5_debug_gemm_trace", "f5_gemm", "f5_attention", "f5_row_norm", "f5_mel_spectrogram",
+    "f5_version", "f5_last_error", "f5_launch_count", "f5_debug_gemm_trace", "f5_debug_attn_trace", "f5_gemm", "f5_attention", "f5_row_norm", "f5_mel_spectrogram",
     "f5_vocos_workspace_bytes", "f5_vocos_decode", "f5_engine_create", "f5_engine_destroy",
     "f5_sample_workspace_bytes", "f5_sample", "f5_sample_flops",
 ]

@@ -2,7 +2,9 @@
 #include "attn.cuh"
 #include "internal.h"
 
+#include <cstdlib>
 namespace f5 {
+static long long* g_attn_trace = nullptr;
 
 int attn_plan(AttnPlan* pl, const void* qkv, void* out, int batches, int seq, int heads, const int* kv_len,
               float scale) {
@@ -21,6 +23,16 @@ int attn_plan(AttnPlan* pl, const void* qkv, void* out, int batches, int seq, in
   pl->p.kv_len = kv_len;
   pl->p.scale_log2 = scale * 1.4426950408889634f;
   pl->p.out = reinterpret_cast<__half*>(out);
+  {
+    static long long* trace = nullptr;
+    static int want = -1;
+    if (want < 0) {
+      want = getenv("F5_ATTN_TRACE") ? 1 : 0;
+      if (want) cudaMalloc(&trace, sizeof(long long) * 16 * 4096);
+    }
+    pl->p.dbg_ts = trace;
+    g_attn_trace = trace;
+  }
   pl->grid = dim3((seq + 2 * kAttnBQ - 1) / (2 * kAttnBQ), heads, batches);
   return 0;
 }
@@ -36,12 +48,19 @@ int attn_configure() {
 
 int attn_run(const AttnPlan& pl, cudaStream_t s) {
   if (int rc = configure_kernels()) return rc;
-  attn_fwd_tcgen05_kernel<<<pl.grid, kAttnThreads, kAttnSmem, s>>>(pl.tm, pl.p);
+  PdlLaunch L(pl.grid, dim3(kAttnThreads), kAttnSmem, s);
+  if (int rc = check_cuda(cudaLaunchKernelEx(&L.cfg, attn_fwd_tcgen05_kernel, pl.tm, pl.p), "attention launch")) return rc;
   count_launch();
   return check_launch("attn_fwd_tcgen05_kernel launch");
 }
 
 }  // namespace f5
+
+extern "C" int f5_debug_attn_trace(long long* host_out, int n_ctas) {
+  if (!f5::g_attn_trace) return -1;
+  cudaDeviceSynchronize();
+  return cudaMemcpy(host_out, f5::g_attn_trace, sizeof(long long) * 16 * (size_t)n_ctas, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -2;
+}
 
 extern "C" int f5_attention(const void* qkv, void* out, int batches, int seq, int heads, const int* kv_len, float scale,
                             f5_stream_t stream) {

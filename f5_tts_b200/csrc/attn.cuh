@@ -21,6 +21,15 @@
 
 namespace f5 {
 
+__device__ __forceinline__ float ex2_approx(float x) {  // one MUFU.EX2; inputs are <= ~8, -inf -> 0
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -43,8 +52,6 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnPar
 
   const int warp = threadIdx.x >> 5;
   const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-  const int kv_len = p.kv_len ? min(p.kv_len[b], p.seq) : p.seq;
-  const int n_kv = (kv_len + kAttnBKV - 1) / kAttnBKV;
   const int q0 = qb * 2 * kAttnBQ;
   const int col_q = h * 64, col_k = p.inner + h * 64, col_v = 2 * p.inner + h * 64;
 
@@ -69,6 +76,10 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnPar
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  pdl_launch_dependents();
+  const int kv_len = p.kv_len ? min(p.kv_len[b], p.seq) : p.seq;
+  const int n_kv = (kv_len + kAttnBKV - 1) / kAttnBKV;
   // columns: S0 [0,128) S1 [128,256) O0 [256,320) O1 [320,384)
 
   if (warp == 0) {
@@ -141,10 +152,20 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnPar
     const uint32_t tmem_O = tmem_base + 256 + w * 64 + lane_off;
     uint8_t* sPw = sP + 2 * w * kAttnTile;
     float m_run = -INFINITY, l_run = 0.0f;
+    long long* ts = p.dbg_ts ? p.dbg_ts + ((long long)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16 + w * 8 : nullptr;
+    long long c_s = 0, c_turn = 0, c_exp = 0, c_o = 0, c_p = 0, c0 = 0, c_begin = 0;
+    if (ts) c_begin = clock64();
+    // Ping-pong turnstile (named barriers 3 + w, 256 threads): the two warpgroups take turns in the exp2-heavy
+    // section, so one warpgroup's MUFU work overlaps the other's tensor-core work instead of both running in lockstep.
+    if (w == 1) named_bar_arrive(3, 256);  // WG0 goes first
     for (int j = 0; j < n_kv; ++j) {
       const int kv_rem = kv_len - j * kAttnBKV;  // valid keys in this tile (>= 1)
+      if (ts) c0 = clock64();
       mbar_wait(&s_full[w], j & 1);
       tc_fence_after();
+      if (ts) { const long long c1 = clock64(); c_s += c1 - c0; c0 = c1; }
+      named_bar_sync(3 + w, 256);
+      if (ts) { const long long c1 = clock64(); c_turn += c1 - c0; c0 = c1; }
       uint32_t r0[32], r1[32], r2[32], r3[32];
       tmem_ld32(tmem_S + 0, r0);
       tmem_ld32(tmem_S + 32, r1);
@@ -172,7 +193,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnPar
       const bool do_rescale = __any_sync(0xffffffffu, grow);
       float alpha = 1.0f;
       if (do_rescale) {
-        alpha = exp2f(m_run - m_new);  // first tile: exp2(-inf) = 0
+        alpha = ex2_approx(m_run - m_new);  // first tile: exp2(-inf) = 0
         m_run = m_new;
       }
       // exponentials -> packed fp16 (kept in registers until the P buffer is free)
@@ -182,7 +203,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnPar
       uint32_t pk[64];
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        float e0 = exp2f(__uint_as_float(r0[2 * i]) * sc - ms), e1 = exp2f(__uint_as_float(r0[2 * i + 1]) * sc - ms);
+        float e0 = ex2_approx(__uint_as_float(r0[2 * i]) * sc - ms), e1 = ex2_approx(__uint_as_float(r0[2 * i + 1]) * sc - ms);
         if (kv_rem < kAttnBKV) {
           if (2 * i >= kv_rem) e0 = 0.f;
           if (2 * i + 1 >= kv_rem) e1 = 0.f;
@@ -192,7 +213,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnPar
       }
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        float e0 = exp2f(__uint_as_float(r1[2 * i]) * sc - ms), e1 = exp2f(__uint_as_float(r1[2 * i + 1]) * sc - ms);
+        float e0 = ex2_approx(__uint_as_float(r1[2 * i]) * sc - ms), e1 = ex2_approx(__uint_as_float(r1[2 * i + 1]) * sc - ms);
         if (kv_rem < kAttnBKV) {
           if (32 + 2 * i >= kv_rem) e0 = 0.f;
           if (32 + 2 * i + 1 >= kv_rem) e1 = 0.f;
@@ -202,7 +223,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnPar
       }
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        float e0 = exp2f(__uint_as_float(r2[2 * i]) * sc - ms), e1 = exp2f(__uint_as_float(r2[2 * i + 1]) * sc - ms);
+        float e0 = ex2_approx(__uint_as_float(r2[2 * i]) * sc - ms), e1 = ex2_approx(__uint_as_float(r2[2 * i + 1]) * sc - ms);
         if (kv_rem < kAttnBKV) {
           if (64 + 2 * i >= kv_rem) e0 = 0.f;
           if (64 + 2 * i + 1 >= kv_rem) e1 = 0.f;
@@ -212,7 +233,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnPar
       }
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        float e0 = exp2f(__uint_as_float(r3[2 * i]) * sc - ms), e1 = exp2f(__uint_as_float(r3[2 * i + 1]) * sc - ms);
+        float e0 = ex2_approx(__uint_as_float(r3[2 * i]) * sc - ms), e1 = ex2_approx(__uint_as_float(r3[2 * i + 1]) * sc - ms);
         if (kv_rem < kAttnBKV) {
           if (96 + 2 * i >= kv_rem) e0 = 0.f;
           if (96 + 2 * i + 1 >= kv_rem) e1 = 0.f;
@@ -221,10 +242,13 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnPar
         pk[48 + i] = pack_half2(e0, e1);
       }
       l_run = l_run * alpha + lsum;
+      named_bar_arrive(3 + (w ^ 1), 256);  // hand the MUFU-heavy section to the other warpgroup
+      if (ts) { const long long c1 = clock64(); c_exp += c1 - c0; c0 = c1; }
       if (j > 0) {
         mbar_wait(&o_full[w], (j - 1) & 1);  // P V of the previous tile retired: P buffer and O are ours
         tc_fence_after();
       }
+      if (ts) { const long long c1 = clock64(); c_o += c1 - c0; c0 = c1; }
       // P -> shared memory, 128B-swizzled K-major: key k lives in sub-tile k/64, 16-byte chunk (k%64)/8
       uint8_t* prow = sPw + row * 128;
 #pragma unroll
@@ -248,6 +272,10 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnPar
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(&p_full[w]);
+      if (ts) c_p += clock64() - c0;
+    }
+    if (ts && row == 0) {
+      ts[0] = c_s; ts[1] = c_turn; ts[2] = c_exp; ts[3] = c_o; ts[4] = c_p; ts[5] = clock64() - c_begin; ts[6] = n_kv;
     }
     // epilogue: O / l -> fp16
     mbar_wait(&o_full[w], (n_kv - 1) & 1);

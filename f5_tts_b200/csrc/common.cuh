@@ -109,6 +109,13 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// Programmatic dependent launch: a kernel launched with the PDL attribute may start while its predecessor is still
+// draining; everything before pdl_wait() (smem carve-up, barrier init, TMEM alloc, descriptor prefetch) overlaps the
+// predecessor's tail.  pdl_wait() returns once the predecessor grid has completed and its writes are visible.
+// Both are no-ops for a normal launch.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ----------------------------------------------------------------------------------------------
 // tcgen05 / TMEM
 // ----------------------------------------------------------------------------------------------

@@ -17,6 +17,8 @@ namespace f5 {
 
 template <int MODE>
 __global__ void __launch_bounds__(256) row_norm_kernel(const NormParams p) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= p.rows) return;
   const int lane = lane_id();
@@ -239,6 +241,8 @@ __global__ void pack_input_kernel(const PackParams p) {
 // ---------------------------------------------------------------------------------------------------------
 
 __global__ void cfg_euler_kernel(const EulerParams p) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int k = *p.step_ptr;
   const float dt = p.dt[k];
   const long long total = (long long)p.BN * p.mel;
@@ -264,7 +268,11 @@ __global__ void cfg_euler_kernel(const EulerParams p) {
   }
 }
 
-__global__ void advance_step_kernel(int* step_ptr) { *step_ptr += 1; }
+__global__ void advance_step_kernel(int* step_ptr) {
+  pdl_wait();
+  pdl_launch_dependents();
+  *step_ptr += 1;
+}
 
 // ---------------------------------------------------------------------------------------------------------
 // Small fp32 linear for the per-sample() conditioning MLPs (modules.py:852-862): out[s, n] = act(in[s,:] . W[n,:] + b)
@@ -323,6 +331,8 @@ __global__ void rope_table_kernel(float* cs, float* sn, int seq, int half) {
 // UNetT (unett.py:271-273): h[b, 0, :] = t_emb[step], h[b, 1:, :] = src[b, :, :]   (fp32)
 __global__ void prepend_time_token_kernel(float* dst, const float* src, const float* t_emb, const int* step_ptr,
                                           int N, int D, long long rows_out) {
+  pdl_wait();
+  pdl_launch_dependents();
   const long long row = blockIdx.x;
   if (row >= rows_out) return;
   const long long b = row / (N + 1);
@@ -333,6 +343,8 @@ __global__ void prepend_time_token_kernel(float* dst, const float* src, const fl
 
 // UNetT skip connection (unett.py:293-295): cat[m, :] = fp16([x[m, :], skip[m, :]])
 __global__ void concat_half_kernel(const float* x, const float* skip, __half* out, long long rows, int D) {
+  pdl_wait();
+  pdl_launch_dependents();
   const long long total = rows * 2 * D;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long m = i / (2 * D);

@@ -244,25 +244,13 @@ f5_gemm_args base_args(long long rows, int n_out, int k, int lda, int ldw, int b
   return a;
 }
 
-// Tile-width heuristic for the persistent GEMM: with one CTA per SM the kernel time is
-// rounds x k-blocks x per-k-block cost, and the per-k-block cost is dominated by the L2 -> SM operand stream
-// ((128 + BN) x 64 fp16 per k-block), so minimise rounds x (128 + BN); ties go to the wider tile (less total traffic).
+// Tile-width heuristic for the persistent GEMM (measured on B200, tools/gemm_sweep.py): the 128x256 tile moves 25 %
+// fewer operand bytes per FLOP and wins (~1.1 PFLOP/s vs ~0.95) once there are at least two full rounds of tiles
+// over the SMs; with fewer tiles the finer 128x128 grid balances better.  BN = 64 never wins.
 int pick_bn(long long rows, int n_out, bool allow256) {
   const long long mt = (rows + 127) / 128;
-  const int sms = num_sms();
-  int best = 128;
-  long long best_cost = -1;
-  for (int bn : {64, 128, 256}) {
-    if (bn == 256 && !allow256) continue;
-    if (bn == 64 && n_out % 64) continue;
-    const long long tiles = mt * ((n_out + bn - 1) / bn);
-    const long long cost = ((tiles + sms - 1) / sms) * (128 + bn);
-    if (best_cost < 0 || cost < best_cost || (cost == best_cost && bn > best)) {
-      best = bn;
-      best_cost = cost;
-    }
-  }
-  return best;
+  if (allow256 && mt * ((n_out + 255) / 256) >= 2LL * num_sms()) return 256;
+  return 128;
 }
 
 int build_step_plans(f5_engine* e, const Layout& L, const f5_sample_args* sa, StepPlans& P) {

@@ -86,7 +86,8 @@ static int launch_inst(const GemmPlan& pl, cudaStream_t s) {
   auto kern = gemm_tcgen05_kernel<BN, STAGES, EPI, ACT, CONV>;
   constexpr size_t smem = gemm_smem_bytes<BN, STAGES>();
   if (int rc = configure_kernels()) return rc;
-  kern<<<pl.grid, kGemmThreads, smem, s>>>(pl.tmA, pl.tmB, pl.tmC, pl.p);
+  PdlLaunch L(pl.grid, dim3(kGemmThreads), smem, s);
+  if (int rc = check_cuda(cudaLaunchKernelEx(&L.cfg, kern, pl.tmA, pl.tmB, pl.tmC, pl.p), "gemm launch")) return rc;
   count_launch();
   return check_launch("gemm_tcgen05_kernel launch");
 }
@@ -109,28 +110,37 @@ static int configure_inst() {
 int configure_kernels() {
   static std::atomic<int> done{0};
   if (done.load()) return 0;
-  if (int rc = configure_inst<64, 8, EPI_F16, ACT_NONE, false>()) return rc;
-  if (int rc = configure_inst<64, 8, EPI_F16, ACT_GELU_TANH, false>()) return rc;
-  if (int rc = configure_inst<64, 8, EPI_F16, ACT_GELU_ERF, false>()) return rc;
-  if (int rc = configure_inst<64, 8, EPI_F32, ACT_NONE, false>()) return rc;
-  if (int rc = configure_inst<64, 8, EPI_RESID, ACT_NONE, false>()) return rc;
-  if (int rc = configure_inst<128, 6, EPI_F16, ACT_NONE, false>()) return rc;
-  if (int rc = configure_inst<128, 6, EPI_F16, ACT_GELU_TANH, false>()) return rc;
-  if (int rc = configure_inst<128, 6, EPI_F16, ACT_GELU_ERF, false>()) return rc;
-  if (int rc = configure_inst<128, 6, EPI_F32, ACT_NONE, false>()) return rc;
-  if (int rc = configure_inst<128, 6, EPI_RESID, ACT_NONE, false>()) return rc;
-  if (int rc = configure_inst<256, 4, EPI_F16, ACT_NONE, false>()) return rc;
-  if (int rc = configure_inst<256, 4, EPI_F16, ACT_GELU_TANH, false>()) return rc;
-  if (int rc = configure_inst<256, 4, EPI_F16, ACT_GELU_ERF, false>()) return rc;
-  if (int rc = configure_inst<256, 4, EPI_F32, ACT_NONE, false>()) return rc;
-  if (int rc = configure_inst<256, 4, EPI_RESID, ACT_NONE, false>()) return rc;
-  if (int rc = configure_inst<128, 6, EPI_QKV_ROPE, ACT_NONE, false>()) return rc;
-  if (int rc = configure_inst<256, 4, EPI_QKV_ROPE, ACT_NONE, false>()) return rc;
-  if (int rc = configure_inst<64, 8, EPI_F16, ACT_MISH, true>()) return rc;
-  if (int rc = configure_inst<64, 8, EPI_RESID, ACT_MISH, true>()) return rc;
+  if (int rc = configure_inst<64, 7, EPI_F16, ACT_NONE, false>()) return rc;
+  if (int rc = configure_inst<64, 7, EPI_F16, ACT_GELU_TANH, false>()) return rc;
+  if (int rc = configure_inst<64, 7, EPI_F16, ACT_GELU_ERF, false>()) return rc;
+  if (int rc = configure_inst<64, 7, EPI_F32, ACT_NONE, false>()) return rc;
+  if (int rc = configure_inst<64, 7, EPI_RESID, ACT_NONE, false>()) return rc;
+  if (int rc = configure_inst<128, 5, EPI_F16, ACT_NONE, false>()) return rc;
+  if (int rc = configure_inst<128, 5, EPI_F16, ACT_GELU_TANH, false>()) return rc;
+  if (int rc = configure_inst<128, 5, EPI_F16, ACT_GELU_ERF, false>()) return rc;
+  if (int rc = configure_inst<128, 5, EPI_F32, ACT_NONE, false>()) return rc;
+  if (int rc = configure_inst<128, 5, EPI_RESID, ACT_NONE, false>()) return rc;
+  if (int rc = configure_inst<256, 3, EPI_F16, ACT_NONE, false>()) return rc;
+  if (int rc = configure_inst<256, 3, EPI_F16, ACT_GELU_TANH, false>()) return rc;
+  if (int rc = configure_inst<256, 3, EPI_F16, ACT_GELU_ERF, false>()) return rc;
+  if (int rc = configure_inst<256, 3, EPI_F32, ACT_NONE, false>()) return rc;
+  if (int rc = configure_inst<256, 3, EPI_RESID, ACT_NONE, false>()) return rc;
+  if (int rc = configure_inst<128, 5, EPI_QKV_ROPE, ACT_NONE, false>()) return rc;
+  if (int rc = configure_inst<256, 3, EPI_QKV_ROPE, ACT_NONE, false>()) return rc;
+  if (int rc = configure_inst<64, 7, EPI_F16, ACT_MISH, true>()) return rc;
+  if (int rc = configure_inst<64, 7, EPI_RESID, ACT_MISH, true>()) return rc;
   if (int rc = attn_configure()) return rc;
   done.store(1);
   return 0;
+}
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("F5_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
 }
 
 int num_sms() {
@@ -144,25 +154,25 @@ int num_sms() {
 }
 
 int gemm_run(const GemmPlan& pl, cudaStream_t s) {
-  F5_GEMM_CASE(64, 8, EPI_F16, ACT_NONE, false)
-  F5_GEMM_CASE(64, 8, EPI_F16, ACT_GELU_TANH, false)
-  F5_GEMM_CASE(64, 8, EPI_F16, ACT_GELU_ERF, false)
-  F5_GEMM_CASE(64, 8, EPI_F32, ACT_NONE, false)
-  F5_GEMM_CASE(64, 8, EPI_RESID, ACT_NONE, false)
-  F5_GEMM_CASE(128, 6, EPI_F16, ACT_NONE, false)
-  F5_GEMM_CASE(128, 6, EPI_F16, ACT_GELU_TANH, false)
-  F5_GEMM_CASE(128, 6, EPI_F16, ACT_GELU_ERF, false)
-  F5_GEMM_CASE(128, 6, EPI_F32, ACT_NONE, false)
-  F5_GEMM_CASE(128, 6, EPI_RESID, ACT_NONE, false)
-  F5_GEMM_CASE(256, 4, EPI_F16, ACT_NONE, false)
-  F5_GEMM_CASE(256, 4, EPI_F16, ACT_GELU_TANH, false)
-  F5_GEMM_CASE(256, 4, EPI_F16, ACT_GELU_ERF, false)
-  F5_GEMM_CASE(256, 4, EPI_F32, ACT_NONE, false)
-  F5_GEMM_CASE(256, 4, EPI_RESID, ACT_NONE, false)
-  F5_GEMM_CASE(128, 6, EPI_QKV_ROPE, ACT_NONE, false)
-  F5_GEMM_CASE(256, 4, EPI_QKV_ROPE, ACT_NONE, false)
-  F5_GEMM_CASE(64, 8, EPI_F16, ACT_MISH, true)
-  F5_GEMM_CASE(64, 8, EPI_RESID, ACT_MISH, true)
+  F5_GEMM_CASE(64, 7, EPI_F16, ACT_NONE, false)
+  F5_GEMM_CASE(64, 7, EPI_F16, ACT_GELU_TANH, false)
+  F5_GEMM_CASE(64, 7, EPI_F16, ACT_GELU_ERF, false)
+  F5_GEMM_CASE(64, 7, EPI_F32, ACT_NONE, false)
+  F5_GEMM_CASE(64, 7, EPI_RESID, ACT_NONE, false)
+  F5_GEMM_CASE(128, 5, EPI_F16, ACT_NONE, false)
+  F5_GEMM_CASE(128, 5, EPI_F16, ACT_GELU_TANH, false)
+  F5_GEMM_CASE(128, 5, EPI_F16, ACT_GELU_ERF, false)
+  F5_GEMM_CASE(128, 5, EPI_F32, ACT_NONE, false)
+  F5_GEMM_CASE(128, 5, EPI_RESID, ACT_NONE, false)
+  F5_GEMM_CASE(256, 3, EPI_F16, ACT_NONE, false)
+  F5_GEMM_CASE(256, 3, EPI_F16, ACT_GELU_TANH, false)
+  F5_GEMM_CASE(256, 3, EPI_F16, ACT_GELU_ERF, false)
+  F5_GEMM_CASE(256, 3, EPI_F32, ACT_NONE, false)
+  F5_GEMM_CASE(256, 3, EPI_RESID, ACT_NONE, false)
+  F5_GEMM_CASE(128, 5, EPI_QKV_ROPE, ACT_NONE, false)
+  F5_GEMM_CASE(256, 3, EPI_QKV_ROPE, ACT_NONE, false)
+  F5_GEMM_CASE(64, 7, EPI_F16, ACT_MISH, true)
+  F5_GEMM_CASE(64, 7, EPI_RESID, ACT_MISH, true)
   set_error("gemm: no kernel instantiated for bn=%d epi=%d act=%d conv=%d", pl.bn, pl.epi, pl.act, pl.conv);
   return -6;
 }
@@ -219,7 +229,7 @@ int gemm_plan(GemmPlan* pl, const void* A, const void* W, const f5_gemm_args* a)
     static int want_trace = -1;
     if (want_trace < 0) {
       want_trace = getenv("F5_GEMM_TRACE") ? 1 : 0;
-      if (want_trace) cudaMalloc(&trace, sizeof(long long) * 8 * 1024);
+      if (want_trace) cudaMalloc(&trace, sizeof(long long) * 16 * 1024);
     }
     p.dbg_ts = trace;
     g_trace = trace;
@@ -286,7 +296,7 @@ unsigned long long f5_launch_count(void) { return f5::g_launches.load(); }
 int f5_debug_gemm_trace(long long* host_out, int n_ctas) {
   if (!f5::g_trace) return -1;
   cudaDeviceSynchronize();
-  return cudaMemcpy(host_out, f5::g_trace, sizeof(long long) * 8 * (size_t)n_ctas, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -2;
+  return cudaMemcpy(host_out, f5::g_trace, sizeof(long long) * 16 * (size_t)n_ctas, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -2;
 }
 
 int f5_gemm(const void* A, const void* W, const f5_gemm_args* args, f5_stream_t stream) {

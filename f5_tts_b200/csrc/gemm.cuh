@@ -26,11 +26,12 @@
 namespace f5 {
 
 constexpr uint32_t kEpiChunkBytes = kBM * 128;  // 128 rows x 128 B (64 fp16 or 32 fp32 columns)
+constexpr int kEpiBufs = 3;                     // staging ring: a bulk store may queue behind operand loads in the TMA unit
 
 template <int BN, int STAGES>
 constexpr size_t gemm_smem_bytes() {
-  return size_t(STAGES) * (kBM * kBK * 2 + BN * kBK * 2) + 2 * kEpiChunkBytes /*epilogue staging*/ +
-         1024 /*align slack*/ + 256 /*barriers*/;
+  return size_t(STAGES) * (kBM * kBK * 2 + BN * kBK * 2) + kEpiBufs * kEpiChunkBytes /*epilogue staging*/ +
+         1024 /*align slack*/ + 256 /*barriers*/ + 2048 /*bias + gate staging*/;
 }
 
 // Values of one 32-column chunk of one accumulator row after bias / RoPE / activation (no store).
@@ -218,15 +219,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * A_BYTES;
-  uint8_t* sC = smem + STAGES * (A_BYTES + B_BYTES);  // 2 x 16 KB epilogue staging (1024-aligned)
-  uint64_t* full = reinterpret_cast<uint64_t*>(sC + 2 * kEpiChunkBytes);
+  uint8_t* sC = smem + STAGES * (A_BYTES + B_BYTES);  // kEpiBufs x 16 KB epilogue staging (1024-aligned)
+  uint64_t* full = reinterpret_cast<uint64_t*>(sC + kEpiBufs * kEpiChunkBytes);
   uint64_t* empty = full + STAGES;
   uint64_t* acc_full = empty + STAGES;  // [2]
   uint64_t* acc_empty = acc_full + 2;   // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* sBias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full) + 256);  // [256] bias of the current tile
+  float* sGate = sBias + 256;                                                         // [256] gate of the current tile
 
   const int warp = threadIdx.x >> 5;
-  long long* ts = p.dbg_ts ? p.dbg_ts + (long long)blockIdx.x * 8 : nullptr;
+  long long* ts = p.dbg_ts ? p.dbg_ts + (long long)blockIdx.x * 16 : nullptr;
   if (ts && threadIdx.x == 0) {
     unsigned long long g;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
@@ -256,6 +259,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();               // predecessor kernel finished: its outputs (our operands) are visible
+  pdl_launch_dependents();  // let the next kernel's prologue overlap our tail
   if (ts && threadIdx.x == 0) ts[2] = clock64();  // setup done
 
   if (warp == 0) {
@@ -324,6 +329,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (EPI == EPI_RESID && p.gate != nullptr)
       gate = p.gate + (p.step_ptr ? (long long)(*p.step_ptr) : 0) * p.gate_step_stride;
     uint32_t tl = 0, chunk_ctr = 0;
+    long long t_accwait = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++tl) {
       const int n0 = (t % tiles_n) * BN;
       const int m0 = ((t / tiles_n) % tiles_m) * kBM;
@@ -338,7 +344,31 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         pos = int(grow % p.seq);
         if (p.row_len != nullptr && row_ok) valid = pos < p.row_len[grow / p.seq];
       }
+      // ---- prefetch everything the epilogue reads from global memory while the main loop of this tile runs ----
+      float4 rope_c[8], rope_s[8];
+      if (EPI != EPI_F32) {
+        named_bar_sync(3, 128);  // every thread is done with the previous tile's sBias / sGate
+        const int et = threadIdx.x - 64;
+#pragma unroll
+        for (int c = et; c < BN; c += 128) {
+          const int n = n0 + c;
+          sBias[c] = (p.bias != nullptr && n < p.n_out) ? __ldg(p.bias + n) : 0.0f;
+          if (EPI == EPI_RESID) sGate[c] = (gate != nullptr && n < p.n_out) ? __ldg(gate + n) : 1.0f;
+        }
+        if (EPI == EPI_QKV_ROPE) {
+          const float4* cs = reinterpret_cast<const float4*>(p.rope_cos + (long long)pos * 32);
+          const float4* sn = reinterpret_cast<const float4*>(p.rope_sin + (long long)pos * 32);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            rope_c[i] = __ldg(cs + i);
+            rope_s[i] = __ldg(sn + i);
+          }
+        }
+      }
+      long long ta0 = 0;
+      if (ts) ta0 = clock64();
       mbar_wait(&acc_full[buf], (tl >> 1) & 1);
+      if (ts) t_accwait += clock64() - ta0;
       if (ts && tl == 0 && threadIdx.x == 64) ts[5] = clock64();  // first accumulator complete
       tc_fence_after();
       const uint32_t tmem_acc = tmem_base + buf * BN + (uint32_t(q * 32) << 16);
@@ -353,27 +383,68 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (row_ok && nc < p.n_out && p.dbg_mode != 3) epilogue_chunk<EPI, ACT>(p, r, nc, grow, pos, valid, gate);
         }
       } else {
-        // staged: 128-byte row chunks -> swizzled smem -> bulk TMA store / reduce-add
-        constexpr int CH_COLS = (EPI == EPI_RESID) ? 32 : 64;
+        // staged: 32-column pieces -> 128-byte row chunks in swizzled smem -> bulk TMA store / reduce-add.
+        // All global reads the epilogue needs (bias, gate, rotary rows) are issued BEFORE the accumulator wait (see
+        // below) and TMEM loads are double-buffered, so no DRAM/L2/TMEM latency sits on the per-chunk path.
+        constexpr int PIECES = BN / 32;
+        constexpr int PPC = (EPI == EPI_RESID) ? 1 : 2;  // pieces per 128-byte chunk
         const int erow = q * 32 + int(lane_id());
         const bool issuer = (threadIdx.x == 64);
-#pragma unroll 1
-        for (int ch = 0; ch < BN / CH_COLS; ++ch, ++chunk_ctr) {
-          uint8_t* sbuf = sC + (chunk_ctr & 1) * kEpiChunkBytes;
-          if (issuer) tma_store_wait_read<1>();  // the store that last used this buffer has drained it
-          named_bar_sync(1, 128);
+        uint32_t ra[32], rb[32];
+        tmem_ld32(tmem_acc, ra);
+#pragma unroll
+        for (int pc = 0; pc < PIECES; ++pc) {
+          uint32_t(&rc)[32] = (pc & 1) ? rb : ra;
+          uint32_t(&rn)[32] = (pc & 1) ? ra : rb;
+          tmem_ld_wait();
+          if (pc + 1 < PIECES) tmem_ld32(tmem_acc + uint32_t((pc + 1) * 32), rn);
+          const int ch = pc / PPC, sub = pc % PPC;
+          uint8_t* sbuf = sC + ((chunk_ctr + ch) % kEpiBufs) * kEpiChunkBytes;
+          if (sub == 0) {
+            if (issuer) tma_store_wait_read<kEpiBufs - 1>();  // the store that last used this buffer drained it
+            named_bar_sync(1, 128);                           // (also publishes sBias / sGate of this tile)
+          }
+          const int ct = pc * 32;  // column inside the tile
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 b = *reinterpret_cast<const float4*>(sBias + ct + 4 * i);
+            v[4 * i + 0] = __uint_as_float(rc[4 * i + 0]) + b.x;
+            v[4 * i + 1] = __uint_as_float(rc[4 * i + 1]) + b.y;
+            v[4 * i + 2] = __uint_as_float(rc[4 * i + 2]) + b.z;
+            v[4 * i + 3] = __uint_as_float(rc[4 * i + 3]) + b.w;
+          }
+          if (EPI == EPI_QKV_ROPE) {
+            const int nc = n0 + ct;
+            const int sec = nc / p.inner, head = (nc % p.inner) / 64;
+            if (sec < 2 && head < p.pe_heads) {
+              // pairs 0..15 of the head for its first 32 columns, pairs 16..31 for the second
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float4 c4 = rope_c[(nc % 64) ? 4 + i : i], s4 = rope_s[(nc % 64) ? 4 + i : i];
+                const float cc[4] = {c4.x, c4.y, c4.z, c4.w}, ss[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float x0 = v[8 * i + 2 * j], x1 = v[8 * i + 2 * j + 1];
+                  v[8 * i + 2 * j] = x0 * cc[j] - x1 * ss[j];
+                  v[8 * i + 2 * j + 1] = x1 * cc[j] + x0 * ss[j];
+                }
+              }
+            }
+          }
+          if (ACT != ACT_NONE) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              if (ACT == ACT_GELU_TANH) v[i] = gelu_tanh(v[i]);
+              if (ACT == ACT_GELU_ERF) v[i] = gelu_erf(v[i]);
+              if (ACT == ACT_MISH) v[i] = mish(v[i]);
+            }
+          }
           uint8_t* srow = sbuf + erow * 128;
           if (EPI == EPI_RESID) {
-            uint32_t r[32];
-            tmem_ld32(tmem_acc + uint32_t(ch * 32), r);
-            tmem_ld_wait();
-            const int nc = n0 + ch * 32;
-            float v[32];
-            epilogue_values<EPI, ACT>(p, r, nc, pos, v);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              float4 g = make_float4(1.f, 1.f, 1.f, 1.f);
-              if (gate != nullptr && nc + 4 * i + 3 < p.n_out) g = __ldg(reinterpret_cast<const float4*>(gate + nc) + i);
+              const float4 g = *reinterpret_cast<const float4*>(sGate + ct + 4 * i);
               float4 o;
               o.x = valid ? g.x * v[4 * i] : 0.f;
               o.y = valid ? g.y * v[4 * i + 1] : 0.f;
@@ -383,41 +454,39 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
           } else {
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              uint32_t r[32];
-              tmem_ld32(tmem_acc + uint32_t(ch * 64 + h * 32), r);
-              tmem_ld_wait();
-              const int nc = n0 + ch * 64 + h * 32;
-              float v[32];
-              epilogue_values<EPI, ACT>(p, r, nc, pos, v);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                uint4 w;
-                w.x = valid ? pack_half2(v[8 * i + 0], v[8 * i + 1]) : 0u;
-                w.y = valid ? pack_half2(v[8 * i + 2], v[8 * i + 3]) : 0u;
-                w.z = valid ? pack_half2(v[8 * i + 4], v[8 * i + 5]) : 0u;
-                w.w = valid ? pack_half2(v[8 * i + 6], v[8 * i + 7]) : 0u;
-                *reinterpret_cast<uint4*>(srow + (((h * 4 + i) ^ (erow & 7)) << 4)) = w;
-              }
+            for (int i = 0; i < 4; ++i) {
+              uint4 w;
+              w.x = valid ? pack_half2(v[8 * i + 0], v[8 * i + 1]) : 0u;
+              w.y = valid ? pack_half2(v[8 * i + 2], v[8 * i + 3]) : 0u;
+              w.z = valid ? pack_half2(v[8 * i + 4], v[8 * i + 5]) : 0u;
+              w.w = valid ? pack_half2(v[8 * i + 6], v[8 * i + 7]) : 0u;
+              *reinterpret_cast<uint4*>(srow + (((sub * 4 + i) ^ (erow & 7)) << 4)) = w;
             }
           }
-          fence_proxy_async_smem();
-          named_bar_sync(2, 128);
-          if (issuer && p.dbg_mode != 3) {
-            const int c0 = n0 + ch * CH_COLS;
-            if (c0 < p.n_out) {
-              if (EPI == EPI_RESID) tma_reduce_add_3d(&tmC, sbuf, c0, m0, bz);
-              else tma_store_3d(&tmC, sbuf, c0, m0, bz);
+          if (sub == PPC - 1) {
+            fence_proxy_async_smem();
+            named_bar_sync(2, 128);
+            if (issuer && p.dbg_mode != 3) {
+              const int c0 = n0 + ch * (32 * PPC);
+              if (c0 < p.n_out) {
+                if (EPI == EPI_RESID) tma_reduce_add_3d(&tmC, sbuf, c0, m0, bz);
+                else tma_store_3d(&tmC, sbuf, c0, m0, bz);
+              }
+              tma_store_commit();
             }
-            tma_store_commit();
           }
         }
+        chunk_ctr += PIECES / PPC;
       }
       tc_fence_before();
       mbar_arrive(&acc_empty[buf]);
     }
-    if (EPI != EPI_F32 && threadIdx.x == 64) tma_store_wait_all();  // smem must outlive the last bulk store
-    if (ts && threadIdx.x == 64) ts[6] = clock64();  // epilogue done
+    if (ts && threadIdx.x == 64) ts[12] = clock64();
+    if (EPI != EPI_F32 && threadIdx.x == 64) tma_store_wait_read<0>();  // smem must outlive the last bulk store
+    if (ts && threadIdx.x == 64) {
+      ts[6] = clock64();  // epilogue done
+      ts[11] = t_accwait;
+    }
   }
 
   tc_fence_before();

@@ -15,6 +15,25 @@ int check_launch(const char* what);
 int configure_kernels();  // cudaFuncSetAttribute for every instantiation (once per process)
 int attn_configure();
 int num_sms();
+bool pdl_enabled();  // F5_PDL=0 disables programmatic dependent launch
+
+// Launch with the programmatic-stream-serialization attribute (PDL); every kernel launched through this helper calls
+// griddepcontrol.wait before touching global memory, so stream order is preserved transitively.
+struct PdlLaunch {
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attr[1];
+  PdlLaunch(dim3 grid, dim3 block, size_t smem, cudaStream_t s) {
+    cfg = cudaLaunchConfig_t{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  }
+};
 
 struct GemmPlan {
   CUtensorMap tmA, tmB, tmC;

@@ -51,6 +51,7 @@ struct AttnParams {
   const int* kv_len;  // [Be] valid keys per sample, or null (= seq)
   float scale_log2;   // softmax scale * log2(e)
   __half* out;        // [Be*seq, inner]
+  long long* dbg_ts;  // optional [CTAs][16] phase-cycle trace (diagnostics; NULL in production)
 };
 
 constexpr int kAttnThreads = 320;   // TMA warp + MMA warp + 2 softmax warpgroups

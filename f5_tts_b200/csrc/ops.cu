@@ -17,14 +17,16 @@ int run_row_norm(int mode, const NormParams& p, cudaStream_t s) {
     set_error("row_norm: D must be a multiple of 128 and <= 1024 (got %d)", p.D);
     return -1;
   }
-  dim3 grid((p.rows + 7) / 8);
-  if (mode == 0) row_norm_kernel<0><<<grid, 256, 0, s>>>(p);
-  else if (mode == 1) row_norm_kernel<1><<<grid, 256, 0, s>>>(p);
-  else if (mode == 2) row_norm_kernel<2><<<grid, 256, 0, s>>>(p);
+  PdlLaunch L(dim3((p.rows + 7) / 8), dim3(256), 0, s);
+  cudaError_t ce;
+  if (mode == 0) ce = cudaLaunchKernelEx(&L.cfg, row_norm_kernel<0>, p);
+  else if (mode == 1) ce = cudaLaunchKernelEx(&L.cfg, row_norm_kernel<1>, p);
+  else if (mode == 2) ce = cudaLaunchKernelEx(&L.cfg, row_norm_kernel<2>, p);
   else {
     set_error("row_norm: bad mode %d", mode);
     return -1;
   }
+  if (int rc = check_cuda(ce, "row_norm launch")) return rc;
   count_launch();
   return check_launch("row_norm_kernel");
 }
@@ -72,8 +74,10 @@ int run_pack_input(const PackParams& p, cudaStream_t s) {
 
 int run_cfg_euler(const EulerParams& p, cudaStream_t s) {
   const long long total = (long long)p.BN * p.mel;
-  cfg_euler_kernel<<<grid_for(total, 256, 148 * 4), 256, 0, s>>>(p);
-  advance_step_kernel<<<1, 1, 0, s>>>(p.step_ptr);
+  PdlLaunch L1(dim3(grid_for(total, 256, 148 * 4)), dim3(256), 0, s);
+  if (int rc = check_cuda(cudaLaunchKernelEx(&L1.cfg, cfg_euler_kernel, p), "cfg_euler launch")) return rc;
+  PdlLaunch L2(dim3(1), dim3(1), 0, s);
+  if (int rc = check_cuda(cudaLaunchKernelEx(&L2.cfg, advance_step_kernel, p.step_ptr), "advance_step launch")) return rc;
   count_launch(2);
   return check_launch("cfg_euler_kernel");
 }
@@ -107,13 +111,17 @@ int run_rope_table(float* cs, float* sn, int seq, int half, cudaStream_t s) {
 
 int run_prepend_time_token(float* dst, const float* src, const float* t_emb, const int* step_ptr, int N, int D,
                            long long rows_out, cudaStream_t s) {
-  prepend_time_token_kernel<<<(unsigned)rows_out, 256, 0, s>>>(dst, src, t_emb, step_ptr, N, D, rows_out);
+  PdlLaunch L(dim3((unsigned)rows_out), dim3(256), 0, s);
+  if (int rc = check_cuda(cudaLaunchKernelEx(&L.cfg, prepend_time_token_kernel, dst, src, t_emb, step_ptr, N, D, rows_out),
+                          "prepend_time_token launch"))
+    return rc;
   count_launch();
   return check_launch("prepend_time_token_kernel");
 }
 
 int run_concat_half(const float* x, const float* skip, __half* out, long long rows, int D, cudaStream_t s) {
-  concat_half_kernel<<<grid_for(rows * 2 * D, 256), 256, 0, s>>>(x, skip, out, rows, D);
+  PdlLaunch L(dim3(grid_for(rows * 2 * D, 256)), dim3(256), 0, s);
+  if (int rc = check_cuda(cudaLaunchKernelEx(&L.cfg, concat_half_kernel, x, skip, out, rows, D), "concat_half launch")) return rc;
   count_launch();
   return check_launch("concat_half_kernel");
 }

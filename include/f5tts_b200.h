@@ -30,6 +30,7 @@ int f5_version(void);
 const char* f5_last_error(void);
 /* diagnostics only: per-CTA clock trace of the last GEMM when the process runs with F5_GEMM_TRACE=1 */
 int f5_debug_gemm_trace(long long* host_out, int n_ctas);
+int f5_debug_attn_trace(long long* host_out, int n_ctas); /* F5_ATTN_TRACE=1 */
 /* number of kernels this library has launched in this process (bench.py reports it as gpu_launches) */
 unsigned long long f5_launch_count(void);
 

@@ -28,7 +28,7 @@ for (M, N, K, epi, act, bn, tag) in ((1876, 3072, 1024, EPI_QKV_ROPE, ACT_NONE, 
     torch.cuda.synchronize()
     ops.linear(a, w, b, **kw)
     n = 148
-    buf = np.zeros((n, 8), dtype=np.int64)
+    buf = np.zeros((n, 16), dtype=np.int64)
     rc = L.f5_debug_gemm_trace(buf.ctypes.data, n)
     t = buf.astype(np.float64)
     g0 = t[:, 0].min()
@@ -37,3 +37,4 @@ for (M, N, K, epi, act, bn, tag) in ((1876, 3072, 1024, EPI_QKV_ROPE, ACT_NONE, 
     print(f"{tag}: CTA start spread {(t[:,0].max()-g0)/1000:.2f} us | setup {np.median(rel(2)):.2f} | first operands {np.median(rel(3)):.2f} | "
           f"MMAs issued {np.median(rel(4)):.2f} (max {rel(4).max():.2f}) | first acc {np.median(rel(5)):.2f} | epilogue done {np.median(rel(6)):.2f} (max {rel(6).max():.2f}) | exit {np.median(rel(7)):.2f} (max {rel(7).max():.2f}) us",
           flush=True)
+    print(f"     wait-acc {np.median(t[:,11])/clk/1000:.2f} us | final drain {np.median(t[:,6]-t[:,12])/clk/1000:.2f} us", flush=True)

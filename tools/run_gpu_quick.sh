@@ -1,6 +1,9 @@
 #!/bin/bash
 mkdir -p gpurun_out
-F5_GEMM_TRACE=1 timeout 200 python tools/gemm_trace.py 2>&1 | tail -8 | tee gpurun_out/gemm_trace.log
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 300 -c 400 --csv --log-file gpurun_out/launches2.csv \
-  python bench.py --steps 1 --warmup 0 --no-cpu-baseline > gpurun_out/ncu_launch_run.log 2>&1
-tail -1 gpurun_out/ncu_launch_run.log | cut -c1-200
+timeout 400 python -m pytest tests/test_gpu_kernels.py -q -m gpu --tb=short 2>&1 | tail -6 | tee gpurun_out/quick_tests.log
+timeout 600 python -m pytest tests/test_gpu_sample.py -q -m gpu --tb=short 2>&1 | tail -8 | tee gpurun_out/quick_tests_sample.log
+for pdl in 1 0; do
+  echo "=== F5_PDL=$pdl"
+  F5_PDL=$pdl timeout 500 python bench.py --steps 5 --warmup 3 --no-cpu-baseline 2>gpurun_out/bench.err | tee gpurun_out/bench_pdl$pdl.json | cut -c1-330
+  tail -3 gpurun_out/bench.err
+done
