@@ -22,7 +22,7 @@ EPI_F16, EPI_F32, EPI_RESID, EPI_QKV_ROPE = 0, 1, 2, 3
 class GemmArgs(C.Structure):
     _fields_ = [
         ("rows", c_int), ("batches", c_int), ("n_out", c_int), ("k", c_int), ("lda", c_int), ("ldw", c_int),
-        ("bn", c_int), ("epi", c_int), ("act", c_int), ("conv_taps", c_int),
+        ("bn", c_int), ("epi", c_int), ("act", c_int), ("conv_taps", c_int), ("cta_pair", c_int),
         ("bias", c_void_p), ("out", c_void_p), ("out16b", c_void_p), ("resid", c_void_p), ("ldo", c_int),
         ("gate", c_void_p), ("step_ptr", c_void_p), ("gate_step_stride", c_ll), ("row_len", c_void_p),
         ("seq", c_int), ("rope_cos", c_void_p), ("rope_sin", c_void_p), ("inner", c_int), ("pe_heads", c_int),

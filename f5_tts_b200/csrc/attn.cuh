@@ -30,6 +30,43 @@ __device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
   asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// 32 scores -> 16 packed fp16 pairs of exp2(s * sc - ms); FULL = every key of the chunk is valid (no masking code)
+template <bool FULL>
+__device__ __forceinline__ void exp_pack32(const uint32_t (&r)[32], int col0, int kv_rem, float sc, float ms,
+                                           float& sum_a, float& sum_b, uint32_t* pk) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    float e0 = ex2_approx(__uint_as_float(r[2 * i]) * sc - ms);
+    float e1 = ex2_approx(__uint_as_float(r[2 * i + 1]) * sc - ms);
+    if (!FULL) {
+      if (col0 + 2 * i >= kv_rem) e0 = 0.f;
+      if (col0 + 2 * i + 1 >= kv_rem) e1 = 0.f;
+    }
+    sum_a += e0;  // two independent accumulation chains
+    sum_b += e1;
+    pk[i] = pack_half2(e0, e1);
+  }
+}
+
+template <bool FULL>
+__device__ __forceinline__ float row_max128(const uint32_t (&r0)[32], const uint32_t (&r1)[32], const uint32_t (&r2)[32],
+                                            const uint32_t (&r3)[32], int kv_rem) {
+  float mx = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    if (FULL) {
+      mx = fmaxf(mx, fmaxf(fmaxf(__uint_as_float(r0[i]), __uint_as_float(r1[i])),
+                           fmaxf(__uint_as_float(r2[i]), __uint_as_float(r3[i]))));
+    } else {
+      if (i < kv_rem) mx = fmaxf(mx, __uint_as_float(r0[i]));
+      if (32 + i < kv_rem) mx = fmaxf(mx, __uint_as_float(r1[i]));
+      if (64 + i < kv_rem) mx = fmaxf(mx, __uint_as_float(r2[i]));
+      if (96 + i < kv_rem) mx = fmaxf(mx, __uint_as_float(r3[i]));
+    }
+  }
+  return mx;
+}
+
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -48,7 +85,8 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnPar
   uint64_t* s_full = v_empty + kAttnStages;        // [2]
   uint64_t* p_full = s_full + 2;                   // [2]
   uint64_t* o_full = p_full + 2;                   // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+  uint64_t* s_free = o_full + 2;                   // [2] softmax has pulled S into registers
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_free + 2);
 
   const int warp = threadIdx.x >> 5;
   const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -68,6 +106,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnPar
       mbar_init(&s_full[w], 1);
       mbar_init(&p_full[w], 128);
       mbar_init(&o_full[w], 1);
+      mbar_init(&s_free[w], 128);
     }
     fence_mbar_init();
   }
@@ -117,6 +156,18 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnPar
       issue_s(1, 0);
       tc_commit(&k_empty[0]);
       for (int j = 0; j < n_kv; ++j) {
+        // S of the NEXT tile is issued as soon as the softmax warps have pulled the current S into registers
+        // (s_free), i.e. long before their exponentials / P are done: the Q K^T latency leaves the softmax chain.
+        if (j + 1 < n_kv) {
+          const int sk = (j + 1) % kAttnStages;
+          mbar_wait(&k_full[sk], ((j + 1) / kAttnStages) & 1);
+          for (int w = 0; w < 2; ++w) {
+            mbar_wait(&s_free[w], j & 1);
+            tc_fence_after();
+            issue_s(w, sk);
+          }
+          tc_commit(&k_empty[sk]);
+        }
         const int sv = j % kAttnStages;
         mbar_wait(&v_full[sv], (j / kAttnStages) & 1);
         for (int w = 0; w < 2; ++w) {
@@ -130,17 +181,8 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnPar
             tc_mma_ss(tmem_base + 256 + w * 64, pdesc, vdesc, idesc_o, (j | kk) != 0);
           }
           tc_commit(&o_full[w]);
-          if (w == 1) tc_commit(&v_empty[sv]);
-          if (j + 1 < n_kv) {
-            const int sk = (j + 1) % kAttnStages;
-            if (w == 0) {
-              mbar_wait(&k_full[sk], ((j + 1) / kAttnStages) & 1);
-              tc_fence_after();
-            }
-            issue_s(w, sk);
-            if (w == 1) tc_commit(&k_empty[sk]);
-          }
         }
+        tc_commit(&v_empty[sv]);
       }
     }
   } else {
@@ -164,29 +206,16 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnPar
       mbar_wait(&s_full[w], j & 1);
       tc_fence_after();
       if (ts) { const long long c1 = clock64(); c_s += c1 - c0; c0 = c1; }
-      named_bar_sync(3 + w, 256);
-      if (ts) { const long long c1 = clock64(); c_turn += c1 - c0; c0 = c1; }
       uint32_t r0[32], r1[32], r2[32], r3[32];
       tmem_ld32(tmem_S + 0, r0);
       tmem_ld32(tmem_S + 32, r1);
       tmem_ld32(tmem_S + 64, r2);
       tmem_ld32(tmem_S + 96, r3);
       tmem_ld_wait();
-      float mx = -INFINITY;
-      if (kv_rem >= kAttnBKV) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-          mx = fmaxf(mx, fmaxf(fmaxf(__uint_as_float(r0[i]), __uint_as_float(r1[i])),
-                               fmaxf(__uint_as_float(r2[i]), __uint_as_float(r3[i]))));
-      } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          if (i < kv_rem) mx = fmaxf(mx, __uint_as_float(r0[i]));
-          if (32 + i < kv_rem) mx = fmaxf(mx, __uint_as_float(r1[i]));
-          if (64 + i < kv_rem) mx = fmaxf(mx, __uint_as_float(r2[i]));
-          if (96 + i < kv_rem) mx = fmaxf(mx, __uint_as_float(r3[i]));
-        }
-      }
+      tc_fence_before();
+      mbar_arrive(&s_free[w]);  // S_w is in registers: the tensor core may overwrite it with the next tile's scores
+      const bool full_tile = kv_rem >= kAttnBKV;  // warp-uniform
+      const float mx = full_tile ? row_max128<true>(r0, r1, r2, r3, kv_rem) : row_max128<false>(r0, r1, r2, r3, kv_rem);
       const float m_new = fmaxf(m_run, mx * p.scale_log2);
       // lazy rescale (warp-uniform decision because tcgen05.ld/st are warp-collective)
       const bool grow = (m_new - m_run) > 8.0f;  // also true on the first tile (m_run = -inf)
@@ -196,51 +225,26 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnPar
         alpha = ex2_approx(m_run - m_new);  // first tile: exp2(-inf) = 0
         m_run = m_new;
       }
+      if (ts) { const long long c1 = clock64(); c_exp += c1 - c0; c0 = c1; }
+      named_bar_sync(3 + w, 256);  // turnstile: only the MUFU-bound exp2 loop is serialised between the warpgroups
+      if (ts) { const long long c1 = clock64(); c_turn += c1 - c0; c0 = c1; }
       // exponentials -> packed fp16 (kept in registers until the P buffer is free)
       const float ms = m_run;
       const float sc = p.scale_log2;
-      float lsum = 0.0f;
+      float lsum = 0.0f, lsum2 = 0.0f;
       uint32_t pk[64];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        float e0 = ex2_approx(__uint_as_float(r0[2 * i]) * sc - ms), e1 = ex2_approx(__uint_as_float(r0[2 * i + 1]) * sc - ms);
-        if (kv_rem < kAttnBKV) {
-          if (2 * i >= kv_rem) e0 = 0.f;
-          if (2 * i + 1 >= kv_rem) e1 = 0.f;
-        }
-        lsum += e0 + e1;
-        pk[i] = pack_half2(e0, e1);
+      if (full_tile) {
+        exp_pack32<true>(r0, 0, kv_rem, sc, ms, lsum, lsum2, pk);
+        exp_pack32<true>(r1, 32, kv_rem, sc, ms, lsum, lsum2, pk + 16);
+        exp_pack32<true>(r2, 64, kv_rem, sc, ms, lsum, lsum2, pk + 32);
+        exp_pack32<true>(r3, 96, kv_rem, sc, ms, lsum, lsum2, pk + 48);
+      } else {
+        exp_pack32<false>(r0, 0, kv_rem, sc, ms, lsum, lsum2, pk);
+        exp_pack32<false>(r1, 32, kv_rem, sc, ms, lsum, lsum2, pk + 16);
+        exp_pack32<false>(r2, 64, kv_rem, sc, ms, lsum, lsum2, pk + 32);
+        exp_pack32<false>(r3, 96, kv_rem, sc, ms, lsum, lsum2, pk + 48);
       }
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        float e0 = ex2_approx(__uint_as_float(r1[2 * i]) * sc - ms), e1 = ex2_approx(__uint_as_float(r1[2 * i + 1]) * sc - ms);
-        if (kv_rem < kAttnBKV) {
-          if (32 + 2 * i >= kv_rem) e0 = 0.f;
-          if (32 + 2 * i + 1 >= kv_rem) e1 = 0.f;
-        }
-        lsum += e0 + e1;
-        pk[16 + i] = pack_half2(e0, e1);
-      }
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        float e0 = ex2_approx(__uint_as_float(r2[2 * i]) * sc - ms), e1 = ex2_approx(__uint_as_float(r2[2 * i + 1]) * sc - ms);
-        if (kv_rem < kAttnBKV) {
-          if (64 + 2 * i >= kv_rem) e0 = 0.f;
-          if (64 + 2 * i + 1 >= kv_rem) e1 = 0.f;
-        }
-        lsum += e0 + e1;
-        pk[32 + i] = pack_half2(e0, e1);
-      }
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        float e0 = ex2_approx(__uint_as_float(r3[2 * i]) * sc - ms), e1 = ex2_approx(__uint_as_float(r3[2 * i + 1]) * sc - ms);
-        if (kv_rem < kAttnBKV) {
-          if (96 + 2 * i >= kv_rem) e0 = 0.f;
-          if (96 + 2 * i + 1 >= kv_rem) e1 = 0.f;
-        }
-        lsum += e0 + e1;
-        pk[48 + i] = pack_half2(e0, e1);
-      }
+      lsum += lsum2;
       l_run = l_run * alpha + lsum;
       named_bar_arrive(3 + (w ^ 1), 256);  // hand the MUFU-heavy section to the other warpgroup
       if (ts) { const long long c1 = clock64(); c_exp += c1 - c0; c0 = c1; }

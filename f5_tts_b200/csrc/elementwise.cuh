@@ -24,14 +24,24 @@ __global__ void __launch_bounds__(256) row_norm_kernel(const NormParams p) {
   const int lane = lane_id();
   const int nv = p.D >> 7;  // float4 per lane (D multiple of 128, <= 1024)
   const float4* xr = reinterpret_cast<const float4*>(p.x + (long long)row * p.D);
-  float4 v[8];
+  const long long so = p.step_ptr ? (long long)(*p.step_ptr) * p.step_stride : 0;
+  const float4* A = reinterpret_cast<const float4*>(p.a + so);
+  const float4* B = (MODE == 2) ? nullptr : reinterpret_cast<const float4*>(p.b + so);
+  float4 v[8], ga[8], gb[8];
   float s = 0.f;
+  // issue every global load up front (row, scale, shift): one exposed L2 latency instead of two
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if (i < nv) v[i] = xr[i * 32 + lane];
 #pragma unroll
   for (int i = 0; i < 8; ++i)
     if (i < nv) {
-      v[i] = xr[i * 32 + lane];
-      s += v[i].x + v[i].y + v[i].z + v[i].w;
+      ga[i] = __ldg(A + i * 32 + lane);
+      if (MODE != 2) gb[i] = __ldg(B + i * 32 + lane);
     }
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if (i < nv) s += v[i].x + v[i].y + v[i].z + v[i].w;
   float mean = 0.f, rstd;
   if (MODE != 2) {
     mean = warp_sum(s) / float(p.D);
@@ -50,23 +60,20 @@ __global__ void __launch_bounds__(256) row_norm_kernel(const NormParams p) {
       if (i < nv) q += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
     rstd = sqrtf(float(p.D)) / fmaxf(sqrtf(warp_sum(q)), 1e-12f);
   }
-  const long long so = p.step_ptr ? (long long)(*p.step_ptr) * p.step_stride : 0;
-  const float4* A = reinterpret_cast<const float4*>(p.a + so);
-  const float4* B = (MODE == 2) ? nullptr : reinterpret_cast<const float4*>(p.b + so);
   uint2* o = reinterpret_cast<uint2*>(p.out + (long long)row * p.D);
 #pragma unroll
   for (int i = 0; i < 8; ++i)
     if (i < nv) {
-      const float4 a = __ldg(A + i * 32 + lane);
+      const float4 a = ga[i];
       float4 r;
       if (MODE == 0) {
-        const float4 b = __ldg(B + i * 32 + lane);
+        const float4 b = gb[i];
         r.x = (v[i].x - mean) * rstd * (1.f + a.x) + b.x;
         r.y = (v[i].y - mean) * rstd * (1.f + a.y) + b.y;
         r.z = (v[i].z - mean) * rstd * (1.f + a.z) + b.z;
         r.w = (v[i].w - mean) * rstd * (1.f + a.w) + b.w;
       } else if (MODE == 1) {
-        const float4 b = __ldg(B + i * 32 + lane);
+        const float4 b = gb[i];
         r.x = (v[i].x - mean) * rstd * a.x + b.x;
         r.y = (v[i].y - mean) * rstd * a.y + b.y;
         r.z = (v[i].z - mean) * rstd * a.z + b.z;
@@ -265,6 +272,16 @@ __global__ void cfg_euler_kernel(const EulerParams p) {
     const __half h = __float2half_rn(yn);
     p.xin[r * p.Kpad + c] = h;
     if (p.packed) p.xin[(r + p.BN) * p.Kpad + c] = h;
+  }
+  // the last CTA to finish advances the device step counter (every CTA has read step k by then)
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    int* done = p.step_ptr + 1;
+    if (atomicAdd(done, 1) == int(gridDim.x) - 1) {
+      *done = 0;
+      *p.step_ptr = k + 1;
+    }
   }
 }
 

@@ -11,6 +11,7 @@
 //  FF1+GELU, FF2 (+gate, +residual)} -> final norm -> proj_out -> fused CFG + Euler update.
 // Every kernel reads the step index from a device counter, so one captured CUDA graph serves all steps.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -244,13 +245,23 @@ f5_gemm_args base_args(long long rows, int n_out, int k, int lda, int ldw, int b
   return a;
 }
 
-// Tile-width heuristic for the persistent GEMM (measured on B200, tools/gemm_sweep.py): the 128x256 tile moves 25 %
-// fewer operand bytes per FLOP and wins (~1.1 PFLOP/s vs ~0.95) once there are at least two full rounds of tiles
-// over the SMs; with fewer tiles the finer 128x128 grid balances better.  BN = 64 never wins.
-int pick_bn(long long rows, int n_out, bool allow256) {
-  const long long mt = (rows + 127) / 128;
-  if (allow256 && mt * ((n_out + 255) / 256) >= 2LL * num_sms()) return 256;
-  return 128;
+// Tile heuristic for the persistent GEMM (measured on B200, tools/gemm_sweep.py, profiles/):
+//  * enough work for >= 2 rounds of 256x256 CTA-pair tiles over the 74 SM pairs -> cta_group::2 256x256
+//    (1.30-1.35 PFLOP/s at M >= 15k: 3/4 of the shared-memory traffic per MMA cycle of the single-CTA kernel);
+//  * otherwise single-CTA 128x128 tiles, which balance better over 148 SMs when there are few tiles
+//    (M = 1876: all variants within 5 %, 128x128 never worse).
+struct TileChoice {
+  int bn, pair;
+};
+TileChoice pick_tile(long long rows, int n_out, bool allow_pair) {
+  const long long pt = ((rows + 255) / 256) * ((n_out + 255) / 256);
+  if (allow_pair && n_out >= 256 && pt >= 2LL * (num_sms() / 2)) return {256, 1};
+  return {128, 0};
+}
+void set_tile(f5_gemm_args& a, long long rows, int n_out, bool allow_pair) {
+  const TileChoice t = pick_tile(rows, n_out, allow_pair);
+  a.bn = t.bn;
+  a.cta_pair = t.pair;
 }
 
 int build_step_plans(f5_engine* e, const Layout& L, const f5_sample_args* sa, StepPlans& P) {
@@ -263,7 +274,7 @@ int build_step_plans(f5_engine* e, const Layout& L, const f5_sample_args* sa, St
   const long long modS = e->modW;
 
   {  // input projection: h0 = xin . proj_w^T + b ; h0h = fp16(mask(h0))
-    f5_gemm_args a = base_args(L.M, D, e->kin, e->kin, e->kin, pick_bn(L.M, D, true), F5_EPI_F32, F5_ACT_NONE);
+    f5_gemm_args a = base_args(L.M, D, e->kin, e->kin, e->kin, 128, F5_EPI_F32, F5_ACT_NONE);
     a.bias = W.proj_b;
     a.out = L.h0;
     a.out16b = L.h0h;
@@ -303,14 +314,14 @@ int build_step_plans(f5_engine* e, const Layout& L, const f5_sample_args* sa, St
   for (int i = 0; i < A.depth; ++i) {
     const f5_layer_weights& lw = W.layers[i];
     if (!dit && lw.w_skip) {
-      f5_gemm_args a = base_args(L.M1, D, 2 * D, 2 * D, 2 * D, pick_bn(L.M1, D, true), F5_EPI_F32, F5_ACT_NONE);
+      f5_gemm_args a = base_args(L.M1, D, 2 * D, 2 * D, 2 * D, 128, F5_EPI_F32, F5_ACT_NONE);
       a.out = L.x;
       a.ldo = D;
       RC(gemm_plan(&P.skip[i], L.cat, lw.w_skip, &a));
     }
     {
-      f5_gemm_args a = base_args(L.M1, 3 * inner, D, D, D, pick_bn(L.M1, 3 * inner, true), F5_EPI_QKV_ROPE, F5_ACT_NONE);
-      if (a.bn == 64) a.bn = 128;
+      f5_gemm_args a = base_args(L.M1, 3 * inner, D, D, D, 128, F5_EPI_QKV_ROPE, F5_ACT_NONE);
+      set_tile(a, L.M1, 3 * inner, true);
       a.bias = lw.b_qkv;
       a.out = L.qkv;
       a.ldo = 3 * inner;
@@ -322,7 +333,8 @@ int build_step_plans(f5_engine* e, const Layout& L, const f5_sample_args* sa, St
       RC(gemm_plan(&P.qkv[i], L.a, lw.w_qkv, &a));
     }
     {
-      f5_gemm_args a = base_args(L.M1, D, inner, inner, inner, pick_bn(L.M1, D, true), F5_EPI_RESID, F5_ACT_NONE);
+      f5_gemm_args a = base_args(L.M1, D, inner, inner, inner, 128, F5_EPI_RESID, F5_ACT_NONE);
+      set_tile(a, L.M1, D, true);
       a.bias = lw.b_out;
       a.resid = L.x;
       a.ldo = D;
@@ -336,14 +348,16 @@ int build_step_plans(f5_engine* e, const Layout& L, const f5_sample_args* sa, St
       RC(gemm_plan(&P.oproj[i], L.ao, lw.w_out, &a));
     }
     {
-      f5_gemm_args a = base_args(L.M1, F, D, D, D, pick_bn(L.M1, F, true), F5_EPI_F16, F5_ACT_GELU_TANH);
+      f5_gemm_args a = base_args(L.M1, F, D, D, D, 128, F5_EPI_F16, F5_ACT_GELU_TANH);
+      set_tile(a, L.M1, F, true);
       a.bias = lw.b_ff1;
       a.out = L.g;
       a.ldo = F;
       RC(gemm_plan(&P.ff1[i], L.a, lw.w_ff1, &a));
     }
     {
-      f5_gemm_args a = base_args(L.M1, D, F, F, F, pick_bn(L.M1, D, true), F5_EPI_RESID, F5_ACT_NONE);
+      f5_gemm_args a = base_args(L.M1, D, F, F, F, 128, F5_EPI_RESID, F5_ACT_NONE);
+      set_tile(a, L.M1, D, true);
       a.bias = lw.b_ff2;
       a.resid = L.x;
       a.ldo = D;
@@ -368,6 +382,13 @@ int build_step_plans(f5_engine* e, const Layout& L, const f5_sample_args* sa, St
   return 0;
 }
 
+// F5_DIAG_SKIP="norm,attn,qkv,out,ff1,ff2,conv" removes kernels from the step schedule (timing decomposition only:
+// results are wrong).  Never set in production.
+static bool diag_skip(const char* what) {
+  static const char* v = getenv("F5_DIAG_SKIP");
+  return v != nullptr && strstr(v, what) != nullptr;
+}
+
 int norm_mod(const f5_engine* e, const Layout& L, const float* x, long long rows, int mode, const float* a,
              const float* b, bool step_indexed, cudaStream_t s) {
   NormParams p{};
@@ -380,6 +401,7 @@ int norm_mod(const f5_engine* e, const Layout& L, const float* x, long long rows
   p.b = b;
   p.step_ptr = step_indexed ? L.step_ptr : nullptr;
   p.step_stride = step_indexed ? e->modW : 0;
+  if (diag_skip("norm")) return 0;
   return run_row_norm(mode, p, s);
 }
 
@@ -388,8 +410,10 @@ int run_step(f5_engine* e, const Layout& L, const f5_sample_args* sa, const Step
   const int D = A.dim;
   const bool dit = A.backbone == 0;
   RC(gemm_run(P.proj, s));
-  RC(gemm_run(P.conv1, s));
-  RC(gemm_run(P.conv2, s));
+  if (!diag_skip("conv")) {
+    RC(gemm_run(P.conv1, s));
+    RC(gemm_run(P.conv2, s));
+  }
   if (!dit) RC(run_prepend_time_token(L.x, L.h0, L.temb, L.step_ptr, L.N, D, L.M1, s));
   const int half = A.depth / 2;
   for (int i = 0; i < A.depth; ++i) {
@@ -407,17 +431,17 @@ int run_step(f5_engine* e, const Layout& L, const f5_sample_args* sa, const Step
       }
       RC(norm_mod(e, L, L.x, L.M1, 2, lw.g_attn, nullptr, false, s));
     }
-    RC(gemm_run(P.qkv[i], s));
-    RC(attn_run(P.attn[0], s));
-    RC(gemm_run(P.oproj[i], s));
+    if (!diag_skip("qkv")) RC(gemm_run(P.qkv[i], s));
+    if (!diag_skip("attn")) RC(attn_run(P.attn[0], s));
+    if (!diag_skip("out")) RC(gemm_run(P.oproj[i], s));
     if (dit) {
       const float* m = L.mod + (size_t)i * 6 * D;
       RC(norm_mod(e, L, L.x, L.M1, 0, m + 4 * D, m + 3 * D, true, s));  // scale_mlp, shift_mlp
     } else {
       RC(norm_mod(e, L, L.x, L.M1, 2, lw.g_ff, nullptr, false, s));
     }
-    RC(gemm_run(P.ff1[i], s));
-    RC(gemm_run(P.ff2[i], s));
+    if (!diag_skip("ff1")) RC(gemm_run(P.ff1[i], s));
+    if (!diag_skip("ff2")) RC(gemm_run(P.ff2[i], s));
   }
   if (dit) {
     const float* m = L.mod + (size_t)A.depth * 6 * D;

@@ -81,21 +81,21 @@ int encode_tmap(CUtensorMap* m, int is_f32, const void* ptr, uint64_t d0, uint64
 int configure_kernels();
 int num_sms();
 
-template <int BN, int STAGES, int EPI, int ACT, bool CONV>
+template <int BN, int STAGES, int EPI, int ACT, bool CONV, bool PAIR = false>
 static int launch_inst(const GemmPlan& pl, cudaStream_t s) {
-  auto kern = gemm_tcgen05_kernel<BN, STAGES, EPI, ACT, CONV>;
-  constexpr size_t smem = gemm_smem_bytes<BN, STAGES>();
+  auto kern = gemm_tcgen05_kernel<BN, STAGES, EPI, ACT, CONV, PAIR>;
+  constexpr size_t smem = gemm_smem_bytes<BN, STAGES, PAIR>();
   if (int rc = configure_kernels()) return rc;
-  PdlLaunch L(pl.grid, dim3(kGemmThreads), smem, s);
+  PdlLaunch L(pl.grid, dim3(kGemmThreads), smem, s, PAIR ? 2 : 1);
   if (int rc = check_cuda(cudaLaunchKernelEx(&L.cfg, kern, pl.tmA, pl.tmB, pl.tmC, pl.p), "gemm launch")) return rc;
   count_launch();
   return check_launch("gemm_tcgen05_kernel launch");
 }
 
-template <int BN, int STAGES, int EPI, int ACT, bool CONV>
+template <int BN, int STAGES, int EPI, int ACT, bool CONV, bool PAIR = false>
 static int configure_inst() {
-  auto kern = gemm_tcgen05_kernel<BN, STAGES, EPI, ACT, CONV>;
-  constexpr size_t smem = gemm_smem_bytes<BN, STAGES>();
+  auto kern = gemm_tcgen05_kernel<BN, STAGES, EPI, ACT, CONV, PAIR>;
+  constexpr size_t smem = gemm_smem_bytes<BN, STAGES, PAIR>();
   if (int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                           "cudaFuncSetAttribute(gemm smem)"))
     return rc;
@@ -103,9 +103,12 @@ static int configure_inst() {
   return 0;
 }
 
-#define F5_GEMM_CASE(BN_, ST_, EPI_, ACT_, CONV_)                                          \
-  if (pl.bn == BN_ && pl.epi == EPI_ && pl.act == ACT_ && (pl.conv != 0) == CONV_)        \
+#define F5_GEMM_CASE(BN_, ST_, EPI_, ACT_, CONV_)                                                        \
+  if (!pl.pair && pl.bn == BN_ && pl.epi == EPI_ && pl.act == ACT_ && (pl.conv != 0) == CONV_)          \
     return launch_inst<BN_, ST_, EPI_, ACT_, CONV_>(pl, s);
+#define F5_GEMM_PAIR_CASE(BN_, ST_, EPI_, ACT_)                                    \
+  if (pl.pair && pl.bn == BN_ && pl.epi == EPI_ && pl.act == ACT_ && !pl.conv)    \
+    return launch_inst<BN_, ST_, EPI_, ACT_, false, true>(pl, s);
 
 int configure_kernels() {
   static std::atomic<int> done{0};
@@ -129,6 +132,14 @@ int configure_kernels() {
   if (int rc = configure_inst<256, 3, EPI_QKV_ROPE, ACT_NONE, false>()) return rc;
   if (int rc = configure_inst<64, 7, EPI_F16, ACT_MISH, true>()) return rc;
   if (int rc = configure_inst<64, 7, EPI_RESID, ACT_MISH, true>()) return rc;
+  if (int rc = configure_inst<256, 5, EPI_F16, ACT_NONE, false, true>()) return rc;
+  if (int rc = configure_inst<256, 5, EPI_F16, ACT_GELU_TANH, false, true>()) return rc;
+  if (int rc = configure_inst<256, 5, EPI_RESID, ACT_NONE, false, true>()) return rc;
+  if (int rc = configure_inst<256, 5, EPI_QKV_ROPE, ACT_NONE, false, true>()) return rc;
+  if (int rc = configure_inst<128, 6, EPI_F16, ACT_NONE, false, true>()) return rc;
+  if (int rc = configure_inst<128, 6, EPI_F16, ACT_GELU_TANH, false, true>()) return rc;
+  if (int rc = configure_inst<128, 6, EPI_RESID, ACT_NONE, false, true>()) return rc;
+  if (int rc = configure_inst<128, 6, EPI_QKV_ROPE, ACT_NONE, false, true>()) return rc;
   if (int rc = attn_configure()) return rc;
   done.store(1);
   return 0;
@@ -173,7 +184,15 @@ int gemm_run(const GemmPlan& pl, cudaStream_t s) {
   F5_GEMM_CASE(256, 3, EPI_QKV_ROPE, ACT_NONE, false)
   F5_GEMM_CASE(64, 7, EPI_F16, ACT_MISH, true)
   F5_GEMM_CASE(64, 7, EPI_RESID, ACT_MISH, true)
-  set_error("gemm: no kernel instantiated for bn=%d epi=%d act=%d conv=%d", pl.bn, pl.epi, pl.act, pl.conv);
+  F5_GEMM_PAIR_CASE(256, 5, EPI_F16, ACT_NONE)
+  F5_GEMM_PAIR_CASE(256, 5, EPI_F16, ACT_GELU_TANH)
+  F5_GEMM_PAIR_CASE(256, 5, EPI_RESID, ACT_NONE)
+  F5_GEMM_PAIR_CASE(256, 5, EPI_QKV_ROPE, ACT_NONE)
+  F5_GEMM_PAIR_CASE(128, 6, EPI_F16, ACT_NONE)
+  F5_GEMM_PAIR_CASE(128, 6, EPI_F16, ACT_GELU_TANH)
+  F5_GEMM_PAIR_CASE(128, 6, EPI_RESID, ACT_NONE)
+  F5_GEMM_PAIR_CASE(128, 6, EPI_QKV_ROPE, ACT_NONE)
+  set_error("gemm: no kernel instantiated for bn=%d epi=%d act=%d conv=%d pair=%d", pl.bn, pl.epi, pl.act, pl.conv, pl.pair);
   return -6;
 }
 
@@ -199,6 +218,7 @@ int gemm_plan(GemmPlan* pl, const void* A, const void* W, const f5_gemm_args* a)
   pl->epi = a->epi;
   pl->act = a->act;
   pl->conv = conv ? 1 : 0;
+  pl->pair = (!conv && a->cta_pair && a->epi != F5_EPI_F32 && (bn == 128 || bn == 256)) ? 1 : 0;
   GemmParams& p = pl->p;
   p.rows = a->rows;
   p.n_out = a->n_out;
@@ -256,7 +276,8 @@ int gemm_plan(GemmPlan* pl, const void* A, const void* W, const f5_gemm_args* a)
     rc = encode_tmap_f16(&pl->tmA, A, (uint64_t)a->k, (uint64_t)a->rows, (uint64_t)a->batches, (uint64_t)a->lda * 2,
                          (uint64_t)a->rows * a->lda * 2, 64, 128, 3);
     if (rc) return rc;
-    rc = encode_tmap_f16(&pl->tmB, W, (uint64_t)a->k, (uint64_t)a->n_out, 1, (uint64_t)a->ldw * 2, 0, 64, (uint32_t)bn, 2);
+    rc = encode_tmap_f16(&pl->tmB, W, (uint64_t)a->k, (uint64_t)a->n_out, 1, (uint64_t)a->ldw * 2, 0, 64,
+                         (uint32_t)(pl->pair ? bn / 2 : bn), 2);
     if (rc) return rc;
   }
   // output tensor map for the staged epilogues (bulk TMA store of fp16 / reduce-add of fp32); columns clip at n_out
@@ -278,6 +299,12 @@ int gemm_plan(GemmPlan* pl, const void* A, const void* W, const f5_gemm_args* a)
     rc = encode_tmap(&pl->tmC, 0, a->out, (uint64_t)a->n_out, (uint64_t)a->rows, (uint64_t)a->batches,
                      (uint64_t)a->ldo * 2, (uint64_t)a->rows * a->ldo * 2, 64, 128, 3);
     if (rc) return rc;
+  }
+  if (pl->pair) {
+    const long long ptiles = (long long)((a->n_out + bn - 1) / bn) * ((a->rows + 2 * kBM - 1) / (2 * kBM)) * a->batches;
+    const long long pairs = num_sms() / 2;
+    pl->grid = dim3((unsigned)(2 * (ptiles < pairs ? ptiles : pairs)), 1, 1);  // persistent CTA pairs
+    return 0;
   }
   const long long tiles = (long long)((a->n_out + bn - 1) / bn) * ((a->rows + kBM - 1) / kBM) * a->batches;
   pl->grid = dim3((unsigned)(tiles < num_sms() ? tiles : num_sms()), 1, 1);  // persistent: one CTA per SM

@@ -28,9 +28,9 @@ namespace f5 {
 constexpr uint32_t kEpiChunkBytes = kBM * 128;  // 128 rows x 128 B (64 fp16 or 32 fp32 columns)
 constexpr int kEpiBufs = 3;                     // staging ring: a bulk store may queue behind operand loads in the TMA unit
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool PAIR = false>
 constexpr size_t gemm_smem_bytes() {
-  return size_t(STAGES) * (kBM * kBK * 2 + BN * kBK * 2) + kEpiBufs * kEpiChunkBytes /*epilogue staging*/ +
+  return size_t(STAGES) * (kBM * kBK * 2 + (PAIR ? BN / 2 : BN) * kBK * 2) + kEpiBufs * kEpiChunkBytes /*epilogue staging*/ +
          1024 /*align slack*/ + 256 /*barriers*/ + 2048 /*bias + gate staging*/;
 }
 
@@ -205,12 +205,19 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
   }
 }
 
-template <int BN, int STAGES, int EPI, int ACT, bool CONV>
+// PAIR = true: cta_group::2.  Two CTAs of a cluster (same TPC) compute one 256 x BN tile: each CTA stages its own 128
+// rows of A and HALF of the W tile (BN/2 rows), the leader CTA issues tcgen05.mma.cta_group::2 (M = 256) for both, and
+// each CTA's accumulator half lands in its own TMEM.  Shared-memory traffic per MMA cycle drops by 1/4 (BN = 256) —
+// the measured limiter of the single-CTA kernel (operand writes by TMA + reads by the tensor core > 128 B/clk).
+template <int BN, int STAGES, int EPI, int ACT, bool CONV, bool PAIR = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
+  static_assert(!(PAIR && CONV), "the conv schedule is single-CTA");
+  constexpr int BNL = PAIR ? BN / 2 : BN;  // W rows staged by this CTA
+  constexpr int TM = PAIR ? 2 * kBM : kBM;  // rows of one (pair-)tile
   constexpr uint32_t A_BYTES = kBM * kBK * 2;
-  constexpr uint32_t B_BYTES = BN * kBK * 2;
+  constexpr uint32_t B_BYTES = BNL * kBK * 2;
   constexpr uint32_t TMEM_COLS = 2 * BN;  // double-buffered accumulator (power of two: 128 / 256 / 512)
   static_assert(BN == 64 || BN == 128 || BN == 256, "BN");
 
@@ -229,6 +236,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   float* sGate = sBias + 256;                                                         // [256] gate of the current tile
 
   const int warp = threadIdx.x >> 5;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0;       // 0 = leader CTA of the pair
+  const int cta_id = PAIR ? int(blockIdx.x >> 1) : int(blockIdx.x);
+  const int cta_step = PAIR ? int(gridDim.x >> 1) : int(gridDim.x);
   long long* ts = p.dbg_ts ? p.dbg_ts + (long long)blockIdx.x * 16 : nullptr;
   if (ts && threadIdx.x == 0) {
     unsigned long long g;
@@ -237,7 +247,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     ts[1] = clock64();
   }
   const int tiles_n = (p.n_out + BN - 1) / BN;
-  const int tiles_m = (p.rows + kBM - 1) / kBM;
+  const int tiles_m = (p.rows + TM - 1) / TM;
   const int num_tiles = tiles_n * tiles_m * p.batches;
 
   if (warp == 0 && elect_one()) {
@@ -250,13 +260,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&acc_full[b], 1);
-      mbar_init(&acc_empty[b], 128);
+      mbar_init(&acc_empty[b], PAIR ? 256 : 128);  // PAIR: both CTAs' epilogue threads arrive on the leader's barrier
     }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  if (warp == 1) {
+    if (PAIR) tmem_alloc_pair(tmem_slot, TMEM_COLS);
+    else tmem_alloc(tmem_slot, TMEM_COLS);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();  // peer barriers are initialised before any remote arrive / multicast commit
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();               // predecessor kernel finished: its outputs (our operands) are visible
@@ -267,9 +281,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (elect_one()) {
       // ===== TMA producer =====
       uint32_t it = 0;  // running k-block counter across tiles -> stage / phase
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      for (int t = cta_id; t < num_tiles; t += cta_step) {
         const int n0 = (t % tiles_n) * BN;
-        const int m0 = ((t / tiles_n) % tiles_m) * kBM;
+        const int m0 = ((t / tiles_n) % tiles_m) * TM + int(rank) * kBM;
         const int bz = t / (tiles_n * tiles_m);
         for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
           const int s = it % STAGES;
@@ -277,6 +291,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           mbar_wait(&empty[s], ph ^ 1);
           if (p.dbg_mode == 1) {
             mbar_arrive(&full[s]);
+            continue;
+          }
+          if (PAIR) {
+            // both CTAs load; every byte is credited to the LEADER's full barrier, which the MMA issuer waits on
+            if (rank == 0) mbar_expect_tx(&full[s], 2 * (A_BYTES + B_BYTES));
+            const uint32_t lbar = mapa_u32(&full[s], 0);
+            tma_load_3d_pair(sA + s * A_BYTES, &tmA, lbar, kb * kBK, m0, bz);
+            tma_load_2d_pair(sB + s * B_BYTES, &tmB, lbar, kb * kBK, n0 + int(rank) * BNL);
             continue;
           }
           mbar_expect_tx(&full[s], A_BYTES + B_BYTES);
@@ -293,11 +315,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    if (elect_one()) {
-      // ===== MMA issuer =====
-      constexpr uint32_t idesc = make_idesc_f16(kBM, BN, 0, 0);
+    if (rank == 0 && elect_one()) {
+      // ===== MMA issuer (leader CTA only when PAIR) =====
+      constexpr uint32_t idesc = make_idesc_f16(TM, BN, 0, 0);
       uint32_t it = 0, tl = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++tl) {
+      for (int t = cta_id; t < num_tiles; t += cta_step, ++tl) {
         const uint32_t buf = tl & 1;
         mbar_wait(&acc_empty[buf], ((tl >> 1) & 1) ^ 1);  // epilogue drained this accumulator
         tc_fence_after();
@@ -314,11 +336,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           for (int k = 0; k < kBK / 16; ++k) {
             if (p.dbg_mode == 2) break;
             // +32 bytes (16 fp16) along K inside the 128B swizzle atom = +2 in the (addr >> 4) field
-            tc_mma_ss(tmem_acc, adesc + uint64_t(k * 2), bdesc + uint64_t(k * 2), idesc, (kb | k) != 0);
+            if (PAIR) tc_mma_ss_pair(tmem_acc, adesc + uint64_t(k * 2), bdesc + uint64_t(k * 2), idesc, (kb | k) != 0);
+            else tc_mma_ss(tmem_acc, adesc + uint64_t(k * 2), bdesc + uint64_t(k * 2), idesc, (kb | k) != 0);
           }
-          tc_commit(&empty[s]);  // smem slot reusable once these MMAs retire
+          if (PAIR) tc_commit_pair(&empty[s]);  // frees the slot in BOTH CTAs once these MMAs retire
+          else tc_commit(&empty[s]);
         }
-        tc_commit(&acc_full[buf]);
+        if (PAIR) tc_commit_pair(&acc_full[buf]);
+        else tc_commit(&acc_full[buf]);
       }
       if (ts) ts[4] = clock64();  // all MMAs issued
     }
@@ -330,9 +355,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       gate = p.gate + (p.step_ptr ? (long long)(*p.step_ptr) : 0) * p.gate_step_stride;
     uint32_t tl = 0, chunk_ctr = 0;
     long long t_accwait = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++tl) {
+    for (int t = cta_id; t < num_tiles; t += cta_step, ++tl) {
       const int n0 = (t % tiles_n) * BN;
-      const int m0 = ((t / tiles_n) % tiles_m) * kBM;
+      const int m0 = ((t / tiles_n) % tiles_m) * TM + int(rank) * kBM;
       const int bz = t / (tiles_n * tiles_m);
       const uint32_t buf = tl & 1;
       const int row_in_batch = m0 + q * 32 + int(lane_id());
@@ -479,7 +504,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         chunk_ctr += PIECES / PPC;
       }
       tc_fence_before();
-      mbar_arrive(&acc_empty[buf]);
+      if (PAIR) mbar_arrive_cluster(mapa_u32(&acc_empty[buf], 0));  // the leader's MMA issuer owns the accumulator ring
+      else mbar_arrive(&acc_empty[buf]);
     }
     if (ts && threadIdx.x == 64) ts[12] = clock64();
     if (EPI != EPI_F32 && threadIdx.x == 64) tma_store_wait_read<0>();  // smem must outlive the last bulk store
@@ -490,9 +516,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();  // the peer may still be consuming our smem / signalling our barriers
+  else __syncthreads();
   if (ts && threadIdx.x == 0) ts[7] = clock64();
-  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+  if (warp == 1) {
+    if (PAIR) tmem_dealloc_pair(tmem_base, TMEM_COLS);
+    else tmem_dealloc(tmem_base, TMEM_COLS);
+  }
 }
 
 }  // namespace f5

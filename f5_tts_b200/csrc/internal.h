@@ -21,17 +21,28 @@ bool pdl_enabled();  // F5_PDL=0 disables programmatic dependent launch
 // griddepcontrol.wait before touching global memory, so stream order is preserved transitively.
 struct PdlLaunch {
   cudaLaunchConfig_t cfg;
-  cudaLaunchAttribute attr[1];
-  PdlLaunch(dim3 grid, dim3 block, size_t smem, cudaStream_t s) {
+  cudaLaunchAttribute attr[2];
+  PdlLaunch(dim3 grid, dim3 block, size_t smem, cudaStream_t s, int cluster_x = 1) {
     cfg = cudaLaunchConfig_t{};
     cfg.gridDim = grid;
     cfg.blockDim = block;
     cfg.dynamicSmemBytes = smem;
     cfg.stream = s;
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    int n = 0;
+    if (cluster_x > 1) {  // CTA pair for cta_group::2 kernels
+      attr[n].id = cudaLaunchAttributeClusterDimension;
+      attr[n].val.clusterDim.x = (unsigned)cluster_x;
+      attr[n].val.clusterDim.y = 1;
+      attr[n].val.clusterDim.z = 1;
+      ++n;
+    }
+    if (pdl_enabled()) {
+      attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[n].val.programmaticStreamSerializationAllowed = 1;
+      ++n;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cfg.numAttrs = n;
   }
 };
 
@@ -39,7 +50,7 @@ struct GemmPlan {
   CUtensorMap tmA, tmB, tmC;
   GemmParams p;
   dim3 grid;
-  int bn, epi, act, conv;
+  int bn, epi, act, conv, pair;
 };
 int gemm_plan(GemmPlan* plan, const void* A, const void* W, const f5_gemm_args* a);
 int gemm_run(const GemmPlan& plan, cudaStream_t s);

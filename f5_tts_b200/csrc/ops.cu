@@ -76,9 +76,7 @@ int run_cfg_euler(const EulerParams& p, cudaStream_t s) {
   const long long total = (long long)p.BN * p.mel;
   PdlLaunch L1(dim3(grid_for(total, 256, 148 * 4)), dim3(256), 0, s);
   if (int rc = check_cuda(cudaLaunchKernelEx(&L1.cfg, cfg_euler_kernel, p), "cfg_euler launch")) return rc;
-  PdlLaunch L2(dim3(1), dim3(1), 0, s);
-  if (int rc = check_cuda(cudaLaunchKernelEx(&L2.cfg, advance_step_kernel, p.step_ptr), "advance_step launch")) return rc;
-  count_launch(2);
+  count_launch(1);
   return check_launch("cfg_euler_kernel");
 }
 

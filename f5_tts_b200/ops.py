@@ -28,7 +28,7 @@ def _need_cuda(*ts):
             raise _lib.F5LibraryError("B200 operators take CUDA tensors only; there is no CPU fallback")
 
 
-def linear(a: torch.Tensor, w: torch.Tensor, bias=None, *, epi=EPI_F16, act=ACT_NONE, bn=0, resid=None, gate=None,
+def linear(a: torch.Tensor, w: torch.Tensor, bias=None, *, epi=EPI_F16, act=ACT_NONE, bn=0, pair=0, resid=None, gate=None,
            row_len=None, seq=0, rope=None, inner=0, pe_heads=0, out16b=False):
     """C = epilogue(a @ w.T).  a fp16 [M, K], w fp16 [N, K] (both contiguous)."""
     _need_cuda(a, w, bias, resid, gate)
@@ -37,6 +37,7 @@ def linear(a: torch.Tensor, w: torch.Tensor, bias=None, *, epi=EPI_F16, act=ACT_
     N = w.shape[0]
     g = _lib.GemmArgs()
     g.rows, g.batches, g.n_out, g.k, g.lda, g.ldw, g.bn, g.epi, g.act = M, 1, N, K, a.stride(0), w.stride(0), bn, epi, act
+    g.cta_pair = pair
     g.bias = _ptr(bias)
     out = None
     out2 = None

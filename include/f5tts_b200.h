@@ -54,6 +54,7 @@ typedef struct {
   int bn;        /* output tile width: 64 | 128 | 256 (0 = pick) */
   int epi, act;
   int conv_taps; /* 0 = plain GEMM */
+  int cta_pair;  /* 1 = 2-CTA (cta_group::2) 256 x bn tiles; bn must be 128 or 256; plain GEMM, not EPI_F32 */
   const float* bias;
   void* out;               /* fp16 (F16 / QKV_ROPE) or fp32 (F32) [batches*rows, ldo] */
   void* out16b;            /* optional fp16 masked copy for F32 */

@@ -49,6 +49,29 @@ def test_gemm_f32(M, N, K, bn):
     assert rel(out, ref) <= 2e-4
 
 
+@pytest.mark.parametrize("M,N,K,bn", [(256, 256, 64, 256), (1876, 2048, 1024, 256), (1876, 3072, 1024, 128), (700, 1024, 2048, 128),
+                                      (129, 512, 192, 256), (30000 // 8, 2048, 1024, 256)])
+def test_gemm_cta_pair(M, N, K, bn):
+    """cta_group::2 tiles (256 x bn per CTA pair): fp16+GELU, fp32 residual reduce-add and QKV+RoPE epilogues."""
+    a, w = gen((M, K), 31), gen((N, K), 32, 1 / math.sqrt(K))
+    bias = gen((N,), 33, 0.5, torch.float32)
+    ref = a.float() @ w.float().t() + bias
+    out = ops.linear(a, w, bias, epi=EPI_F16, act=ACT_GELU_TANH, bn=bn, pair=1)
+    report(f"pair f16 gelu {M}x{N}x{K} bn{bn}", out, F.gelu(ref, approximate="tanh"))
+    assert rel(out, F.gelu(ref, approximate="tanh")) <= 1.5e-3
+    x0 = gen((M, N), 34, 1.0, torch.float32)
+    gate = gen((N,), 35, 0.5, torch.float32)
+    x = x0.clone()
+    ops.linear(a, w, bias, epi=EPI_RESID, bn=bn, pair=1, resid=x, gate=gate)
+    assert rel(x, x0 + gate * ref) <= 2e-4
+    if N % 192 == 0:
+        seq, inner = M // 2, N // 3
+        cs, sn = ops.rope_tables(seq, DEV)
+        o = ops.linear(a[: 2 * seq], w, bias, epi=EPI_QKV_ROPE, bn=bn, pair=1, seq=seq, rope=(cs, sn), inner=inner, pe_heads=1)
+        o1 = ops.linear(a[: 2 * seq], w, bias, epi=EPI_QKV_ROPE, bn=128, seq=seq, rope=(cs, sn), inner=inner, pe_heads=1)
+        assert rel(o, o1) <= 1e-6  # same arithmetic as the single-CTA kernel
+
+
 @pytest.mark.parametrize("act", [ACT_NONE, ACT_GELU_TANH, ACT_GELU_ERF])
 @pytest.mark.parametrize("bn", [64, 128, 256])
 def test_gemm_f16_act(act, bn):

@@ -99,6 +99,22 @@ def test_sample_vs_oracle(variant):
     assert r <= TOL
 
 
+def test_large_batch_uses_cta_pair_gemms():
+    """B = 8 x 938 frames (BASELINE config 4 shape per GPU, M = 15008): the engine switches to the cta_group::2
+    256x256 GEMM tiles; one Euler step against the CPU oracle."""
+    cfg = O.f5tts_base()
+    model, sd = build(cfg, 1234)
+    g = torch.Generator().manual_seed(21)
+    cond = torch.randn(8, 282, 100, generator=g)
+    text = torch.randint(0, 2545, (8, 150), generator=g)
+    kw = dict(steps=1, cfg_strength=2.0, sway_sampling_coef=-1.0, seed=5, use_epss=False)
+    ref = O.sample(sd, cfg, cond, text, 938, **kw)
+    out, traj = model.sample(cond.to(DEV), text.to(DEV), 938, **kw, y0=ref.y0.to(DEV))
+    r = rel(traj[1], ref.trajectory[1])
+    print(f"[large-batch/pair] step rel-L2 {r:.3e}")
+    assert r <= TOL
+
+
 def test_graph_equals_eager_and_deterministic():
     cfg = O.f5tts_base()
     model, _ = build(cfg, 1234)

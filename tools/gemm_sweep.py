@@ -12,11 +12,11 @@ torch.cuda.init()
 g = torch.Generator().manual_seed(0)
 
 
-def bench(M, N, K, epi, act, bn, nw=24, rounds=4):
+def bench(M, N, K, epi, act, bn, nw=24, rounds=4, pair=0):
     a = [torch.randn(M, K, generator=g).half().to(DEV) for _ in range(2)]
     w = [(torch.randn(N, K, generator=g) / 32).half().to(DEV) for _ in range(nw)]
     b = torch.randn(N, generator=g).to(DEV)
-    kw = dict(epi=epi, act=act, bn=bn)
+    kw = dict(epi=epi, act=act, bn=bn, pair=pair)
     if epi == EPI_RESID:
         kw["resid"] = torch.zeros(M, N, device=DEV)
         kw["gate"] = torch.randn(N, generator=g).to(DEV)
@@ -54,4 +54,7 @@ for M in ((1876, 30000) if os.environ.get('F5_GEMM_DBG') else (1876, 15008, 3000
             nw = 24 if M < 2000 else 6
             us, tf = bench(M, N, K, epi, act, bn, nw=nw, rounds=3)
             row.append(f"bn{bn}: {us:7.1f}us {tf:6.0f}TF")
+        for bn in (128, 256):
+            us, tf = bench(M, N, K, epi, act, bn, nw=24 if M < 2000 else 6, rounds=3, pair=1)
+            row.append(f"PAIR{bn}: {us:7.1f}us {tf:6.0f}TF")
         print(f"M={M:6d} {tag:7s} N={N:5d} K={K:5d} | " + " | ".join(row), flush=True)
