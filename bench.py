@@ -151,34 +151,67 @@ def hot_path(model, voc, wav, text, duration, lens, nfe, frames0=None):
     return out, audio
 
 
-def isolated_gemm_roofline(M, peaks, dev):
-    """Dominant kernel alone: FF1 GEMM (M x 2048 x 1024, bias + GELU-tanh epilogue), 48 distinct weight matrices
-    (192 MB > L2) launched back to back, CUDA events on the launching stream."""
-    from f5_tts_b200 import ops
-
-    N, K, nw = 2048, 1024, 48
-    g = torch.Generator().manual_seed(3)
-    a = [torch.randn(M, K, generator=g).half().to(dev) for _ in range(4)]
-    w = [(torch.randn(N, K, generator=g) / 32).half().to(dev) for _ in range(nw)]
-    b = torch.randn(N, generator=g).to(dev)
-    for i in range(nw):
-        ops.linear(a[i % 4], w[i], b, epi=ops.EPI_F16, act=ops.ACT_GELU_TANH, bn=128)
+def _graph_time_us(fn, n_launch, rounds=5):
+    """Average device time per launch of `fn` (which enqueues n_launch kernels): captured into a CUDA graph so that
+    host-side launch cost (ctypes + tensor-map encoding) is not in the measurement; CUDA events on the launching stream."""
+    fn()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        fn()
+    for _ in range(2):
+        g.replay()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    rounds = 5
     e0.record()
     for _ in range(rounds):
-        for i in range(nw):
-            ops.linear(a[i % 4], w[i], b, epi=ops.EPI_F16, act=ops.ACT_GELU_TANH, bn=128)
+        g.replay()
     e1.record()
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / (rounds * nw)
-    flops = 2.0 * M * N * K
-    ach = flops / (ms * 1e-3) / 1e12
-    return dict(bound="tensor", kernel="gemm_tcgen05_kernel<BN=128,STAGES=3,EPI_F16,GELU_TANH> (FF1)",
-                shape=[M, N, K], us_per_launch=round(ms * 1e3, 2), achieved=round(ach, 1), peak=peaks["tf"],
-                unit="TFLOP/s", frac=round(ach / peaks["tf"], 4), peak_source=peaks["src"] + " bf16_tflops (burst)",
-                flops_per_launch=flops, traffic=load_traffic())
+    return e0.elapsed_time(e1) * 1e3 / (rounds * n_launch)
+
+
+def isolated_gemm_roofline(M, seq, peaks, dev):
+    """Dominant kernel alone: FF1 GEMM (M x 2048 x 1024, bias + GELU-tanh epilogue), 48 distinct weight matrices
+    (192 MB > L2) launched back to back from a CUDA graph, CUDA events on the launching stream.  Also times the other
+    GEMM shapes of a block and the attention kernel the same way (`kernels`)."""
+    from f5_tts_b200 import ops
+
+    nw = 48
+    g = torch.Generator().manual_seed(3)
+    pair = 1 if ((M + 255) // 256) * 8 >= 148 else 0  # same rule as the engine (pick_tile)
+    bn = 256 if pair else 128
+
+    def run(N, K, epi, act, tag, n_w=nw, **kw):
+        a = [torch.randn(M, K, generator=g).half().to(dev) for _ in range(2)]
+        w = [(torch.randn(N, K, generator=g) / 32).half().to(dev) for _ in range(n_w)]
+        b = torch.randn(N, generator=g).to(dev)
+        if epi == ops.EPI_RESID:
+            kw["resid"] = torch.zeros(M, N, device=dev)
+            kw["gate"] = torch.randn(N, generator=g).to(dev)
+        us = _graph_time_us(lambda: [ops.linear(a[i % 2], w[i], b, epi=epi, act=act, bn=bn, pair=pair, **kw)
+                                     for i in range(n_w)], n_w)
+        fl = 2.0 * M * N * K
+        return dict(kernel=tag, shape=[M, N, K], us_per_launch=round(us, 2), tflops=round(fl / us / 1e6, 1),
+                    frac=round(fl / us / 1e6 / peaks["tf"], 4))
+
+    rows = [run(2048, 1024, ops.EPI_F16, ops.ACT_GELU_TANH, "FF1 (bias+GELU-tanh, fp16 out)"),
+            run(3072, 1024, ops.EPI_QKV_ROPE, ops.ACT_NONE, "QKV (bias+RoPE)", n_w=24, seq=seq,
+                rope=ops.rope_tables(seq, dev), inner=1024, pe_heads=1),
+            run(1024, 1024, ops.EPI_RESID, ops.ACT_NONE, "out-proj (gate, TMA reduce-add)"),
+            run(1024, 2048, ops.EPI_RESID, ops.ACT_NONE, "FF2 (gate, TMA reduce-add)")]
+    qkv = [torch.randn(M, 3072, generator=g).half().to(dev) for _ in range(3)]
+    us = _graph_time_us(lambda: [ops.attention(qkv[i % 3], M // seq, seq, 16) for i in range(12)], 12)
+    afl = 4.0 * (M // seq) * 16 * seq * seq * 64
+    rows.append(dict(kernel="attention (dh 64, non-causal)", shape=[M // seq, seq, 16], us_per_launch=round(us, 2),
+                     tflops=round(afl / us / 1e6, 1), frac=round(afl / us / 1e6 / peaks["tf"], 4)))
+    ff1 = rows[0]
+    return dict(bound="tensor",
+                kernel=f"gemm_tcgen05_kernel<BN={bn},{'cta_group::2 pair' if pair else 'cta_group::1'},EPI_F16,GELU_TANH> (FF1)",
+                shape=ff1["shape"], us_per_launch=ff1["us_per_launch"], achieved=ff1["tflops"], peak=peaks["tf"],
+                unit="TFLOP/s", frac=ff1["frac"], peak_source=peaks["src"] + " bf16_tflops (burst)",
+                flops_per_launch=2.0 * M * 2048 * 1024, traffic=load_traffic(), kernels=rows,
+                method="48 launches over distinct weights (192 MB > L2) replayed from a CUDA graph, CUDA events")
 
 
 def load_traffic():
@@ -366,7 +399,7 @@ def main():
     line = None
     if rank == 0:
         flops = model.transformer.sample_flops(w["B"], max(w["frames"]), nfe, CFG_STRENGTH)
-        roof = isolated_gemm_roofline(2 * w["B"] * max(w["frames"]), peaks, dev)
+        roof = isolated_gemm_roofline(2 * w["B"] * max(w["frames"]), max(w["frames"]), peaks, dev)
         step_tf = flops / (ms * 1e-3) / 1e12
         roof["step_tensor"] = dict(flops_per_step=flops, achieved=round(step_tf, 1), peak=peaks["tf_sus"],
                                    unit="TFLOP/s", frac=round(step_tf / peaks["tf_sus"], 4),

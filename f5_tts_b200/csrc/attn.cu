@@ -24,6 +24,14 @@ int attn_plan(AttnPlan* pl, const void* qkv, void* out, int batches, int seq, in
   pl->p.scale_log2 = scale * 1.4426950408889634f;
   pl->p.out = reinterpret_cast<__half*>(out);
   {
+    static int ts = -1;
+    if (ts < 0) {
+      const char* e = getenv("F5_ATTN_TURNSTILE");
+      ts = e ? atoi(e) : 1;  // measured: 22.6 us (on) vs 24.4 us (off) at Be=2, seq=938
+    }
+    pl->p.turnstile = ts;
+  }
+  {
     static long long* trace = nullptr;
     static int want = -1;
     if (want < 0) {

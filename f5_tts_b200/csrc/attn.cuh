@@ -194,24 +194,37 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnPar
     const uint32_t tmem_O = tmem_base + 256 + w * 64 + lane_off;
     uint8_t* sPw = sP + 2 * w * kAttnTile;
     float m_run = -INFINITY, l_run = 0.0f;
+#ifdef F5_TRACE
     long long* ts = p.dbg_ts ? p.dbg_ts + ((long long)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16 + w * 8 : nullptr;
-    long long c_s = 0, c_turn = 0, c_exp = 0, c_o = 0, c_p = 0, c0 = 0, c_begin = 0;
+#endif
+#ifdef F5_TRACE
+    long long c_s = 0, c_turn = 0, c_exp = 0, c_o = 0, c_p = 0, c0 = 0, c_begin = 0, c_ld = 0;
+#endif
+#ifdef F5_TRACE
     if (ts) c_begin = clock64();
+#endif
     // Ping-pong turnstile (named barriers 3 + w, 256 threads): the two warpgroups take turns in the exp2-heavy
     // section, so one warpgroup's MUFU work overlaps the other's tensor-core work instead of both running in lockstep.
-    if (w == 1) named_bar_arrive(3, 256);  // WG0 goes first
+    if (p.turnstile && w == 1) named_bar_arrive(3, 256);  // WG0 goes first
     for (int j = 0; j < n_kv; ++j) {
       const int kv_rem = kv_len - j * kAttnBKV;  // valid keys in this tile (>= 1)
+#ifdef F5_TRACE
       if (ts) c0 = clock64();
+#endif
       mbar_wait(&s_full[w], j & 1);
       tc_fence_after();
+#ifdef F5_TRACE
       if (ts) { const long long c1 = clock64(); c_s += c1 - c0; c0 = c1; }
+#endif
       uint32_t r0[32], r1[32], r2[32], r3[32];
       tmem_ld32(tmem_S + 0, r0);
       tmem_ld32(tmem_S + 32, r1);
       tmem_ld32(tmem_S + 64, r2);
       tmem_ld32(tmem_S + 96, r3);
       tmem_ld_wait();
+#ifdef F5_TRACE
+      if (ts) { const long long c1 = clock64(); c_ld += c1 - c0; c0 = c1; }
+#endif
       tc_fence_before();
       mbar_arrive(&s_free[w]);  // S_w is in registers: the tensor core may overwrite it with the next tile's scores
       const bool full_tile = kv_rem >= kAttnBKV;  // warp-uniform
@@ -225,9 +238,13 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnPar
         alpha = ex2_approx(m_run - m_new);  // first tile: exp2(-inf) = 0
         m_run = m_new;
       }
+#ifdef F5_TRACE
       if (ts) { const long long c1 = clock64(); c_exp += c1 - c0; c0 = c1; }
-      named_bar_sync(3 + w, 256);  // turnstile: only the MUFU-bound exp2 loop is serialised between the warpgroups
+#endif
+      if (p.turnstile) named_bar_sync(3 + w, 256);  // only the MUFU-bound exp2 loop is serialised between the warpgroups
+#ifdef F5_TRACE
       if (ts) { const long long c1 = clock64(); c_turn += c1 - c0; c0 = c1; }
+#endif
       // exponentials -> packed fp16 (kept in registers until the P buffer is free)
       const float ms = m_run;
       const float sc = p.scale_log2;
@@ -246,13 +263,17 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnPar
       }
       lsum += lsum2;
       l_run = l_run * alpha + lsum;
-      named_bar_arrive(3 + (w ^ 1), 256);  // hand the MUFU-heavy section to the other warpgroup
+      if (p.turnstile) named_bar_arrive(3 + (w ^ 1), 256);  // hand the MUFU-heavy section to the other warpgroup
+#ifdef F5_TRACE
       if (ts) { const long long c1 = clock64(); c_exp += c1 - c0; c0 = c1; }
+#endif
       if (j > 0) {
         mbar_wait(&o_full[w], (j - 1) & 1);  // P V of the previous tile retired: P buffer and O are ours
         tc_fence_after();
       }
+#ifdef F5_TRACE
       if (ts) { const long long c1 = clock64(); c_o += c1 - c0; c0 = c1; }
+#endif
       // P -> shared memory, 128B-swizzled K-major: key k lives in sub-tile k/64, 16-byte chunk (k%64)/8
       uint8_t* prow = sPw + row * 128;
 #pragma unroll
@@ -276,11 +297,15 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnPar
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(&p_full[w]);
+#ifdef F5_TRACE
       if (ts) c_p += clock64() - c0;
+#endif
     }
+#ifdef F5_TRACE
     if (ts && row == 0) {
-      ts[0] = c_s; ts[1] = c_turn; ts[2] = c_exp; ts[3] = c_o; ts[4] = c_p; ts[5] = clock64() - c_begin; ts[6] = n_kv;
+      ts[0] = c_s; ts[1] = c_turn; ts[2] = c_exp; ts[3] = c_o; ts[4] = c_p; ts[5] = clock64() - c_begin; ts[6] = n_kv; ts[7] = c_ld;
     }
+#endif
     // epilogue: O / l -> fp16
     mbar_wait(&o_full[w], (n_kv - 1) & 1);
     tc_fence_after();

@@ -239,13 +239,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const uint32_t rank = PAIR ? cluster_ctarank() : 0;       // 0 = leader CTA of the pair
   const int cta_id = PAIR ? int(blockIdx.x >> 1) : int(blockIdx.x);
   const int cta_step = PAIR ? int(gridDim.x >> 1) : int(gridDim.x);
+#ifdef F5_TRACE
   long long* ts = p.dbg_ts ? p.dbg_ts + (long long)blockIdx.x * 16 : nullptr;
+#endif
+#ifdef F5_TRACE
   if (ts && threadIdx.x == 0) {
     unsigned long long g;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
     ts[0] = (long long)g;
     ts[1] = clock64();
   }
+#endif
   const int tiles_n = (p.n_out + BN - 1) / BN;
   const int tiles_m = (p.rows + TM - 1) / TM;
   const int num_tiles = tiles_n * tiles_m * p.batches;
@@ -275,7 +279,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();               // predecessor kernel finished: its outputs (our operands) are visible
   pdl_launch_dependents();  // let the next kernel's prologue overlap our tail
+#ifdef F5_TRACE
   if (ts && threadIdx.x == 0) ts[2] = clock64();  // setup done
+#endif
 
   if (warp == 0) {
     if (elect_one()) {
@@ -328,7 +334,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&full[s], ph);
+#ifdef F5_TRACE
           if (ts && it == 0) ts[3] = clock64();  // first operands landed
+#endif
           tc_fence_after();
           const uint64_t adesc = make_smem_desc_sw128(smem_u32(sA + s * A_BYTES));
           const uint64_t bdesc = make_smem_desc_sw128(smem_u32(sB + s * B_BYTES));
@@ -345,7 +353,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (PAIR) tc_commit_pair(&acc_full[buf]);
         else tc_commit(&acc_full[buf]);
       }
+#ifdef F5_TRACE
       if (ts) ts[4] = clock64();  // all MMAs issued
+#endif
     }
   } else {
     // ===== epilogue: warps 2..5 -> TMEM lane quarters 2,3,0,1 =====
@@ -354,7 +364,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (EPI == EPI_RESID && p.gate != nullptr)
       gate = p.gate + (p.step_ptr ? (long long)(*p.step_ptr) : 0) * p.gate_step_stride;
     uint32_t tl = 0, chunk_ctr = 0;
+#ifdef F5_TRACE
     long long t_accwait = 0;
+#endif
     for (int t = cta_id; t < num_tiles; t += cta_step, ++tl) {
       const int n0 = (t % tiles_n) * BN;
       const int m0 = ((t / tiles_n) % tiles_m) * TM + int(rank) * kBM;
@@ -390,11 +402,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
         }
       }
+#ifdef F5_TRACE
       long long ta0 = 0;
+#endif
+#ifdef F5_TRACE
       if (ts) ta0 = clock64();
+#endif
       mbar_wait(&acc_full[buf], (tl >> 1) & 1);
+#ifdef F5_TRACE
       if (ts) t_accwait += clock64() - ta0;
+#endif
+#ifdef F5_TRACE
       if (ts && tl == 0 && threadIdx.x == 64) ts[5] = clock64();  // first accumulator complete
+#endif
       tc_fence_after();
       const uint32_t tmem_acc = tmem_base + buf * BN + (uint32_t(q * 32) << 16);
       if (EPI == EPI_F32) {
@@ -507,18 +527,24 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (PAIR) mbar_arrive_cluster(mapa_u32(&acc_empty[buf], 0));  // the leader's MMA issuer owns the accumulator ring
       else mbar_arrive(&acc_empty[buf]);
     }
+#ifdef F5_TRACE
     if (ts && threadIdx.x == 64) ts[12] = clock64();
+#endif
     if (EPI != EPI_F32 && threadIdx.x == 64) tma_store_wait_read<0>();  // smem must outlive the last bulk store
+#ifdef F5_TRACE
     if (ts && threadIdx.x == 64) {
       ts[6] = clock64();  // epilogue done
       ts[11] = t_accwait;
     }
+#endif
   }
 
   tc_fence_before();
   if (PAIR) cluster_sync_all();  // the peer may still be consuming our smem / signalling our barriers
   else __syncthreads();
+#ifdef F5_TRACE
   if (ts && threadIdx.x == 0) ts[7] = clock64();
+#endif
   if (warp == 1) {
     if (PAIR) tmem_dealloc_pair(tmem_base, TMEM_COLS);
     else tmem_dealloc(tmem_base, TMEM_COLS);

@@ -52,6 +52,7 @@ struct AttnParams {
   float scale_log2;   // softmax scale * log2(e)
   __half* out;        // [Be*seq, inner]
   long long* dbg_ts;  // optional [CTAs][16] phase-cycle trace (diagnostics; NULL in production)
+  int turnstile;      // 1: serialise the exp2 loops of the two softmax warpgroups (ping-pong); 0: free-running
 };
 
 constexpr int kAttnThreads = 320;   // TMA warp + MMA warp + 2 softmax warpgroups

@@ -1,31 +1,33 @@
 #!/bin/bash
-# One GPU visit: parity tests, bench line, ncu launch list, ncu full captures of the two tensor-core kernels.
+# One GPU visit: parity tests, smoke, bench line (+ reference arm), ncu launch list, ncu full captures.
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv | tee gpurun_out/gpu.txt
 if [ "${SKIP_TESTS:-0}" != "1" ]; then
 for f in tests/test_gpu_kernels.py tests/test_gpu_sample.py; do
   b=$(basename $f .py)
   echo "=== $f"
-  timeout 600 python -m pytest $f -q -m gpu -s --tb=short 2>&1 | tail -${TAILN:-70} | tee gpurun_out/$b.log
+  timeout 900 python -m pytest $f -q -m gpu -s --tb=short 2>&1 | tail -${TAILN:-70} | tee gpurun_out/$b.log
 done
 fi
 echo "=== smoke"
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -5 | tee gpurun_out/smoke.log
 echo "=== bench"
-timeout 600 python bench.py ${BENCH_ARGS} 2> gpurun_out/bench.err | tee gpurun_out/bench.json
+timeout 900 python bench.py ${BENCH_ARGS} 2> gpurun_out/bench.err | tee gpurun_out/bench.json
 tail -5 gpurun_out/bench.err
+echo "=== bench --impl reference"
+timeout 600 python bench.py --impl reference --steps 1 --warmup 0 2> gpurun_out/bench_ref.err | tee gpurun_out/bench_reference.json | cut -c1-400
 if [ "${SKIP_NCU:-0}" != "1" ]; then
 echo "=== ncu launch list"
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 300 -c 700 --csv --log-file gpurun_out/launches.csv \
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 200 -c 520 --csv --log-file gpurun_out/launches.csv \
   python bench.py --steps 1 --warmup 0 --no-cpu-baseline > gpurun_out/ncu_launch_run.log 2>&1
-tail -2 gpurun_out/ncu_launch_run.log
-echo "=== ncu full: gemm"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_tcgen05 -s 120 -c 6 -o gpurun_out/prof_gemm -f \
+tail -1 gpurun_out/ncu_launch_run.log | cut -c1-200
+echo "=== ncu full: gemm (one block's four GEMMs)"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_tcgen05 -s 60 -c 5 -o gpurun_out/prof_gemm -f \
   python bench.py --steps 1 --warmup 0 --no-cpu-baseline > gpurun_out/ncu_gemm_run.log 2>&1
-tail -2 gpurun_out/ncu_gemm_run.log
-echo "=== ncu full: attention"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:attn_fwd -s 10 -c 2 -o gpurun_out/prof_attn -f \
+tail -2 gpurun_out/ncu_gemm_run.log | cut -c1-200
+echo "=== ncu full: attention + row_norm"
+timeout 900 ncu --set full --clock-control none --import-source on -k "regex:attn_fwd|row_norm" -s 12 -c 3 -o gpurun_out/prof_attn -f \
   python bench.py --steps 1 --warmup 0 --no-cpu-baseline > gpurun_out/ncu_attn_run.log 2>&1
-tail -2 gpurun_out/ncu_attn_run.log
+tail -2 gpurun_out/ncu_attn_run.log | cut -c1-200
 fi
 ls -la gpurun_out
