@@ -11,7 +11,7 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libf5tts_b200.so")
+LIB_PATH = os.environ.get("F5_LIB") or os.path.join(_HERE, "libf5tts_b200.so")  # F5_LIB: diagnostic (trace) build
 
 c_void_p, c_int, c_float, c_size_t, c_ll = C.c_void_p, C.c_int, C.c_float, C.c_size_t, C.c_longlong
 
@@ -100,6 +100,7 @@ def lib():
         L.f5_last_error.restype = C.c_char_p
         L.f5_launch_count.restype = C.c_ulonglong
         L.f5_gemm.argtypes = [c_void_p, c_void_p, C.POINTER(GemmArgs), c_void_p]
+        L.f5_gemm_tile.argtypes = [C.POINTER(GemmArgs), C.POINTER(c_int), C.POINTER(c_int)]
         L.f5_attention.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_float, c_void_p]
         L.f5_row_norm.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p]
         L.f5_mel_spectrogram.argtypes = [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p]
@@ -115,7 +116,7 @@ def lib():
         L.f5_sample.argtypes = [c_void_p, C.POINTER(SampleArgs), c_void_p, c_size_t, c_void_p]
         L.f5_sample_flops.argtypes = [c_void_p, c_int, c_int, c_int, c_float]
         L.f5_sample_flops.restype = C.c_double
-        for name in ("f5_gemm", "f5_attention", "f5_row_norm", "f5_mel_spectrogram", "f5_vocos_decode",
+        for name in ("f5_gemm", "f5_gemm_tile", "f5_attention", "f5_row_norm", "f5_mel_spectrogram", "f5_vocos_decode",
                      "f5_engine_create", "f5_sample"):
             getattr(L, name).restype = c_int
         _lib = L
@@ -133,7 +134,7 @@ def launch_count() -> int:
 
 
 EXPORTED_SYMBOLS = [
-    "f5_version", "f5_last_error", "f5_launch_count", "f5_debug_gemm_trace", "f5_debug_attn_trace", "f5_gemm", "f5_attention", "f5_row_norm", "f5_mel_spectrogram",
+    "f5_version", "f5_last_error", "f5_launch_count", "f5_debug_gemm_trace", "f5_debug_attn_trace", "f5_gemm", "f5_gemm_tile", "f5_attention", "f5_row_norm", "f5_mel_spectrogram",
     "f5_vocos_workspace_bytes", "f5_vocos_decode", "f5_engine_create", "f5_engine_destroy",
     "f5_sample_workspace_bytes", "f5_sample", "f5_sample_flops",
 ]

@@ -30,12 +30,6 @@ int attn_plan(AttnPlan* pl, const void* qkv, void* out, int batches, int seq, in
       ts = e ? atoi(e) : 1;  // measured: 22.6 us (on) vs 24.4 us (off) at Be=2, seq=938
     }
     pl->p.turnstile = ts;
-    static int var = -1;
-    if (var < 0) {
-      const char* e = getenv("F5_ATTN_VARIANT");
-      var = e ? atoi(e) : 3;
-    }
-    pl->p.variant = var;
   }
   {
     static long long* trace = nullptr;
@@ -57,24 +51,13 @@ int attn_configure() {
                           "cudaFuncSetAttribute(attn smem)"))
     return rc;
   cudaFuncSetAttribute(attn_fwd_tcgen05_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-  if (int rc = check_cuda(cudaFuncSetAttribute(attn_fwd_tcgen05_kernel_v4, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               (int)kAttnSmem),
-                          "cudaFuncSetAttribute(attn v4 smem)"))
-    return rc;
-  cudaFuncSetAttribute(attn_fwd_tcgen05_kernel_v4, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   return 0;
 }
 
 int attn_run(const AttnPlan& pl, cudaStream_t s) {
   if (int rc = configure_kernels()) return rc;
-  if (pl.p.variant == 4) {
-    PdlLaunch L(pl.grid, dim3(kAttn4Threads), kAttnSmem, s);
-    if (int rc = check_cuda(cudaLaunchKernelEx(&L.cfg, attn_fwd_tcgen05_kernel_v4, pl.tm, pl.p), "attention v4 launch"))
-      return rc;
-  } else {
-    PdlLaunch L(pl.grid, dim3(kAttnThreads), kAttnSmem, s);
-    if (int rc = check_cuda(cudaLaunchKernelEx(&L.cfg, attn_fwd_tcgen05_kernel, pl.tm, pl.p), "attention launch")) return rc;
-  }
+  PdlLaunch L(pl.grid, dim3(kAttnThreads), kAttnSmem, s);
+  if (int rc = check_cuda(cudaLaunchKernelEx(&L.cfg, attn_fwd_tcgen05_kernel, pl.tm, pl.p), "attention launch")) return rc;
   count_launch();
   return check_launch("attn_fwd_tcgen05_kernel launch");
 }

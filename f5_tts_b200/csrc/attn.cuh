@@ -198,7 +198,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnPar
     long long* ts = p.dbg_ts ? p.dbg_ts + ((long long)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16 + w * 8 : nullptr;
 #endif
 #ifdef F5_TRACE
-    long long c_s = 0, c_turn = 0, c_exp = 0, c_o = 0, c_p = 0, c0 = 0, c_begin = 0, c_ld = 0;
+    long long c_s = 0, c_turn = 0, c_exp = 0, c_o = 0, c_p = 0, c0 = 0, c_begin = 0, c_ld = 0, c_max = 0;
 #endif
 #ifdef F5_TRACE
     if (ts) c_begin = clock64();
@@ -239,7 +239,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnPar
         m_run = m_new;
       }
 #ifdef F5_TRACE
-      if (ts) { const long long c1 = clock64(); c_exp += c1 - c0; c0 = c1; }
+      if (ts) { const long long c1 = clock64(); c_max += c1 - c0; c0 = c1; }
 #endif
       if (p.turnstile) named_bar_sync(3 + w, 256);  // only the MUFU-bound exp2 loop is serialised between the warpgroups
 #ifdef F5_TRACE
@@ -303,7 +303,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnPar
     }
 #ifdef F5_TRACE
     if (ts && row == 0) {
-      ts[0] = c_s; ts[1] = c_turn; ts[2] = c_exp; ts[3] = c_o; ts[4] = c_p; ts[5] = clock64() - c_begin; ts[6] = n_kv; ts[7] = c_ld;
+      ts[0] = c_s; ts[1] = c_turn; ts[2] = c_exp; ts[3] = c_o; ts[4] = c_p; ts[5] = clock64() - c_begin; ts[6] = c_max; ts[7] = c_ld;
     }
 #endif
     // epilogue: O / l -> fp16
@@ -327,241 +327,6 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnPar
           wv.w = pack_half2(__uint_as_float(r[8 * g + 6]) * inv_l, __uint_as_float(r[8 * g + 7]) * inv_l);
           reinterpret_cast<uint4*>(o)[g] = wv;
         }
-      }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 512);
-}
-
-
-// v4: TWO threads per query row (each owns 64 of the 128 keys of a tile) -> 16 softmax warps (4 per SM sub-partition):
-// the exp2 stream of one query tile is fed by two warps per scheduler, which keeps MUFU busy while the partner warps
-// wait on barriers / TMEM, and every per-tile dependency chain is half as long.
-__global__ void __launch_bounds__(kAttn4Threads, 1)
-attn_fwd_tcgen05_kernel_v4(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
-  uint8_t* sQ = smem;                              // 2 tiles
-  uint8_t* sK = sQ + 2 * kAttnTile;                // kAttnStages tiles
-  uint8_t* sV = sK + kAttnStages * kAttnTile;      // kAttnStages tiles
-  uint8_t* sP = sV + kAttnStages * kAttnTile;      // 2 warpgroups x 2 sub-tiles
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 4 * kAttnTile);
-  uint64_t* q_full = bars;                         // [1]
-  uint64_t* k_full = q_full + 1;                   // [stages]
-  uint64_t* k_empty = k_full + kAttnStages;        // [stages]
-  uint64_t* v_full = k_empty + kAttnStages;        // [stages]
-  uint64_t* v_empty = v_full + kAttnStages;        // [stages]
-  uint64_t* s_full = v_empty + kAttnStages;        // [2]
-  uint64_t* p_full = s_full + 2;                   // [2]
-  uint64_t* o_full = p_full + 2;                   // [2]
-  uint64_t* s_free = o_full + 2;                   // [2] softmax has pulled S into registers
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_free + 2);
-  float* sXch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);  // [2 buf][2 WG][2 half][128] row max / sum exchange
-
-  const int warp = threadIdx.x >> 5;
-  const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-  const int q0 = qb * 2 * kAttnBQ;
-  const int col_q = h * 64, col_k = p.inner + h * 64, col_v = 2 * p.inner + h * 64;
-
-  if (warp == 0 && elect_one()) {
-    tma_prefetch_desc(&tmQKV);
-    mbar_init(q_full, 1);
-    for (int s = 0; s < kAttnStages; ++s) {
-      mbar_init(&k_full[s], 1);
-      mbar_init(&k_empty[s], 1);
-      mbar_init(&v_full[s], 1);
-      mbar_init(&v_empty[s], 1);
-    }
-    for (int w = 0; w < 2; ++w) {
-      mbar_init(&s_full[w], 1);
-      mbar_init(&p_full[w], 256);
-      mbar_init(&o_full[w], 1);
-      mbar_init(&s_free[w], 256);
-    }
-    fence_mbar_init();
-  }
-  if (warp == 1) tmem_alloc(tmem_slot, 512);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  pdl_wait();
-  pdl_launch_dependents();
-  const int kv_len = p.kv_len ? min(p.kv_len[b], p.seq) : p.seq;
-  const int n_kv = (kv_len + kAttnBKV - 1) / kAttnBKV;
-  // columns: S0 [0,128) S1 [128,256) O0 [256,320) O1 [320,384)
-
-  if (warp == 0) {
-    if (elect_one()) {
-      mbar_expect_tx(q_full, 2 * kAttnTile);
-      tma_load_3d(sQ, &tmQKV, q_full, col_q, q0, b);
-      tma_load_3d(sQ + kAttnTile, &tmQKV, q_full, col_q, q0 + kAttnBQ, b);
-      for (int j = 0; j < n_kv; ++j) {
-        const int s = j % kAttnStages;
-        const uint32_t ph = (j / kAttnStages) & 1;
-        mbar_wait(&k_empty[s], ph ^ 1);
-        mbar_expect_tx(&k_full[s], kAttnTile);
-        tma_load_3d(sK + s * kAttnTile, &tmQKV, &k_full[s], col_k, j * kAttnBKV, b);
-        mbar_wait(&v_empty[s], ph ^ 1);
-        mbar_expect_tx(&v_full[s], kAttnTile);
-        tma_load_3d(sV + s * kAttnTile, &tmQKV, &v_full[s], col_v, j * kAttnBKV, b);
-      }
-    }
-  } else if (warp == 1) {
-    if (elect_one()) {
-      constexpr uint32_t idesc_s = make_idesc_f16(128, 128, 0, 0);  // S = Q K^T : both K-major
-      constexpr uint32_t idesc_o = make_idesc_f16(128, 64, 0, 1);   // O = P V   : V is MN-major
-      auto issue_s = [&](int w, int ks) {
-        const uint64_t qdesc = make_smem_desc_sw128(smem_u32(sQ + w * kAttnTile));
-        const uint64_t kdesc = make_smem_desc_sw128(smem_u32(sK + ks * kAttnTile));
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          tc_mma_ss(tmem_base + w * 128, qdesc + uint64_t(2 * k), kdesc + uint64_t(2 * k), idesc_s, k != 0);
-        tc_commit(&s_full[w]);
-      };
-      mbar_wait(q_full, 0);
-      mbar_wait(&k_full[0], 0);
-      tc_fence_after();
-      issue_s(0, 0);
-      issue_s(1, 0);
-      tc_commit(&k_empty[0]);
-      for (int j = 0; j < n_kv; ++j) {
-        // S of the NEXT tile is issued as soon as the softmax warps have pulled the current S into registers
-        // (s_free), i.e. long before their exponentials / P are done: the Q K^T latency leaves the softmax chain.
-        if (j + 1 < n_kv) {
-          const int sk = (j + 1) % kAttnStages;
-          mbar_wait(&k_full[sk], ((j + 1) / kAttnStages) & 1);
-          for (int w = 0; w < 2; ++w) {
-            mbar_wait(&s_free[w], j & 1);
-            tc_fence_after();
-            issue_s(w, sk);
-          }
-          tc_commit(&k_empty[sk]);
-        }
-        const int sv = j % kAttnStages;
-        mbar_wait(&v_full[sv], (j / kAttnStages) & 1);
-        for (int w = 0; w < 2; ++w) {
-          mbar_wait(&p_full[w], j & 1);
-          tc_fence_after();
-#pragma unroll
-          for (int kk = 0; kk < 8; ++kk) {
-            const uint64_t pdesc =
-                make_smem_desc_sw128(smem_u32(sP + (2 * w + (kk >> 2)) * kAttnTile)) + uint64_t(2 * (kk & 3));
-            const uint64_t vdesc = make_smem_desc_sw128(smem_u32(sV + sv * kAttnTile + kk * 16 * 128));
-            tc_mma_ss(tmem_base + 256 + w * 64, pdesc, vdesc, idesc_o, (j | kk) != 0);
-          }
-          tc_commit(&o_full[w]);
-        }
-        tc_commit(&v_empty[sv]);
-      }
-    }
-  } else {
-    const int sw = warp - 2;       // 0..15
-    const int w = sw >> 3;         // query tile / warpgroup pair 0 / 1
-    const int hf = (sw >> 2) & 1;  // which 64-key half of every tile this thread owns
-    const int q = warp & 3;        // TMEM lane quarter
-    const int row = q * 32 + int(lane_id());
-    const uint32_t lane_off = uint32_t(q * 32) << 16;
-    const uint32_t tmem_S = tmem_base + w * 128 + hf * 64 + lane_off;
-    const uint32_t tmem_O = tmem_base + 256 + w * 64 + hf * 32 + lane_off;  // this thread's 32 of the 64 output columns
-    uint8_t* prow = sP + (2 * w + hf) * kAttnTile + row * 128;               // half hf of P == swizzled sub-tile hf
-    const int pair_bar = 5 + w * 4 + q;                                      // the two warps that share these 32 rows
-    float m_run = -INFINITY, l_run = 0.0f;
-    for (int j = 0; j < n_kv; ++j) {
-      const int my_rem = kv_len - j * kAttnBKV - hf * 64;  // valid keys in my half of this tile (may be <= 0)
-      mbar_wait(&s_full[w], j & 1);
-      tc_fence_after();
-      uint32_t r0[32], r1[32];
-      tmem_ld32(tmem_S + 0, r0);
-      tmem_ld32(tmem_S + 32, r1);
-      tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive(&s_free[w]);  // my half of S_w is in registers
-      const bool full = my_rem >= 64;  // warp-uniform
-      float mx = -INFINITY;
-      if (full) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(r0[i]), __uint_as_float(r1[i])));
-      } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          if (i < my_rem) mx = fmaxf(mx, __uint_as_float(r0[i]));
-          if (32 + i < my_rem) mx = fmaxf(mx, __uint_as_float(r1[i]));
-        }
-      }
-      float* xch = sXch + (j & 1) * 512 + w * 256;
-      xch[hf * 128 + row] = mx;
-      named_bar_sync(pair_bar, 64);
-      mx = fmaxf(mx, xch[(hf ^ 1) * 128 + row]);
-      const float m_new = fmaxf(m_run, mx * p.scale_log2);
-      const bool grow = (m_new - m_run) > 8.0f;  // identical in both threads of a row; true on the first tile
-      const bool do_rescale = __any_sync(0xffffffffu, grow);
-      float alpha = 1.0f;
-      if (do_rescale) {
-        alpha = ex2_approx(m_run - m_new);
-        m_run = m_new;
-      }
-      if (j > 0) {
-        mbar_wait(&o_full[w], (j - 1) & 1);  // P V of the previous tile retired: P buffer and O are ours
-        tc_fence_after();
-      }
-      const float ms = m_run, sc = p.scale_log2;
-      float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-      for (int g = 0; g < 8; ++g) {  // 8 keys -> one 16-byte chunk of the swizzled row
-        float e[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int c = g * 8 + i;
-          const float sv = __uint_as_float(c < 32 ? r0[c & 31] : r1[c & 31]);
-          e[i] = ex2_approx(sv * sc - ms);
-          if (!full && c >= my_rem) e[i] = 0.f;
-        }
-        s0 += (e[0] + e[2]) + (e[4] + e[6]);
-        s1 += (e[1] + e[3]) + (e[5] + e[7]);
-        const uint4 wv = make_uint4(pack_half2(e[0], e[1]), pack_half2(e[2], e[3]), pack_half2(e[4], e[5]),
-                                    pack_half2(e[6], e[7]));
-        *reinterpret_cast<uint4*>(prow + ((g ^ (row & 7)) << 4)) = wv;
-      }
-      l_run = l_run * alpha + (s0 + s1);
-      if (do_rescale && j > 0) {
-        uint32_t r[32];
-        tmem_ld32(tmem_O, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
-        tmem_st32(tmem_O, r);
-        tmem_st_wait();
-      }
-      fence_proxy_async_smem();
-      tc_fence_before();
-      mbar_arrive(&p_full[w]);
-    }
-    // epilogue: O / l -> fp16; the row sum is split over the two threads of the row
-    float* xch = sXch + (n_kv & 1) * 512 + w * 256;
-    xch[hf * 128 + row] = l_run;
-    named_bar_sync(pair_bar, 64);
-    const float inv_l = 1.0f / (l_run + xch[(hf ^ 1) * 128 + row]);
-    mbar_wait(&o_full[w], (n_kv - 1) & 1);
-    tc_fence_after();
-    const int qrow = q0 + w * kAttnBQ + row;
-    uint32_t r[32];
-    tmem_ld32(tmem_O, r);
-    tmem_ld_wait();
-    if (qrow < p.seq) {
-      __half* o = p.out + ((long long)b * p.seq + qrow) * p.inner + h * 64 + hf * 32;
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        uint4 wv;
-        wv.x = pack_half2(__uint_as_float(r[8 * g + 0]) * inv_l, __uint_as_float(r[8 * g + 1]) * inv_l);
-        wv.y = pack_half2(__uint_as_float(r[8 * g + 2]) * inv_l, __uint_as_float(r[8 * g + 3]) * inv_l);
-        wv.z = pack_half2(__uint_as_float(r[8 * g + 4]) * inv_l, __uint_as_float(r[8 * g + 5]) * inv_l);
-        wv.w = pack_half2(__uint_as_float(r[8 * g + 6]) * inv_l, __uint_as_float(r[8 * g + 7]) * inv_l);
-        reinterpret_cast<uint4*>(o)[g] = wv;
       }
     }
   }

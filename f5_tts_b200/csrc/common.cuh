@@ -60,8 +60,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// non-blocking phase test (acquire): lets one thread multiplex several producer/consumer streams
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+
 // generic-proxy smem writes -> visible to the async proxy (TMA / tcgen05 operand reads)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
 // ----------------------------------------------------------------------------------------------
 // TMA (cp.async.bulk.tensor), tile mode, mbarrier completion
@@ -269,10 +281,13 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 // ----------------------------------------------------------------------------------------------
 // math
 // ----------------------------------------------------------------------------------------------
-__device__ __forceinline__ float gelu_tanh(float x) {  // F.gelu(approximate="tanh") = x * sigmoid(2u)
-  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
-  const float u = k0 * (x + k1 * x * x * x);
-  return __fdividef(x, 1.0f + __expf(-2.0f * u));
+__device__ __forceinline__ float gelu_tanh(float x) {  // F.gelu(approximate="tanh") = x * sigmoid(2u), u = k0 (x + k1 x^3)
+  // exp(-2u) = 2^(x * (c0 + c1 x^2)) with the constants folded: 3 FMA-pipe ops + MUFU.EX2 + FADD + MUFU.RCP + FMUL
+  const float c0 = -2.3022081981f;   // -2 * sqrt(2/pi) * log2(e)
+  const float c1 = -0.1029432396f;   // c0 * 0.044715
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * fmaf(x * x, c1, c0)));
+  return __fdividef(x, 1.0f + e);
 }
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.7071067811865476f)); }
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }

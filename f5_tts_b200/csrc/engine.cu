@@ -250,18 +250,10 @@ f5_gemm_args base_args(long long rows, int n_out, int k, int lda, int ldw, int b
 //    (1.30-1.35 PFLOP/s at M >= 15k: 3/4 of the shared-memory traffic per MMA cycle of the single-CTA kernel);
 //  * otherwise single-CTA 128x128 tiles, which balance better over 148 SMs when there are few tiles
 //    (M = 1876: all variants within 5 %, 128x128 never worse).
-struct TileChoice {
-  int bn, pair;
-};
-TileChoice pick_tile(long long rows, int n_out, bool allow_pair) {
-  const long long pt = ((rows + 255) / 256) * ((n_out + 255) / 256);
-  if (allow_pair && n_out >= 256 && pt >= 2LL * (num_sms() / 2)) return {256, 1};
-  return {128, 0};
-}
-void set_tile(f5_gemm_args& a, long long rows, int n_out, bool allow_pair) {
-  const TileChoice t = pick_tile(rows, n_out, allow_pair);
-  a.bn = t.bn;
-  a.cta_pair = t.pair;
+// bn = 0: the GEMM planner picks the tile shape (gemm.cu: pick_tile)
+void set_tile(f5_gemm_args& a, long long, int, bool) {
+  a.bn = 0;
+  a.cta_pair = 0;
 }
 
 int build_step_plans(f5_engine* e, const Layout& L, const f5_sample_args* sa, StepPlans& P) {

@@ -86,7 +86,7 @@ static int launch_inst(const GemmPlan& pl, cudaStream_t s) {
   auto kern = gemm_tcgen05_kernel<BN, STAGES, EPI, ACT, CONV, PAIR>;
   constexpr size_t smem = gemm_smem_bytes<BN, STAGES, PAIR>();
   if (int rc = configure_kernels()) return rc;
-  PdlLaunch L(pl.grid, dim3(kGemmThreads), smem, s, PAIR ? 2 : 1);
+  PdlLaunch L(pl.grid, dim3(gemm_threads(ACT)), smem, s, PAIR ? 2 : 1);
   if (int rc = check_cuda(cudaLaunchKernelEx(&L.cfg, kern, pl.tmA, pl.tmB, pl.tmC, pl.p), "gemm launch")) return rc;
   count_launch();
   return check_launch("gemm_tcgen05_kernel launch");
@@ -129,6 +129,10 @@ int configure_kernels() {
   if (int rc = configure_inst<256, 3, EPI_F32, ACT_NONE, false>()) return rc;
   if (int rc = configure_inst<256, 3, EPI_RESID, ACT_NONE, false>()) return rc;
   if (int rc = configure_inst<128, 5, EPI_QKV_ROPE, ACT_NONE, false>()) return rc;
+  if (int rc = configure_inst<192, 4, EPI_QKV_ROPE, ACT_NONE, false>()) return rc;
+  if (int rc = configure_inst<192, 4, EPI_F16, ACT_NONE, false>()) return rc;
+  if (int rc = configure_inst<192, 4, EPI_F16, ACT_GELU_TANH, false>()) return rc;
+  if (int rc = configure_inst<192, 4, EPI_RESID, ACT_NONE, false>()) return rc;
   if (int rc = configure_inst<256, 3, EPI_QKV_ROPE, ACT_NONE, false>()) return rc;
   if (int rc = configure_inst<64, 7, EPI_F16, ACT_MISH, true>()) return rc;
   if (int rc = configure_inst<64, 7, EPI_RESID, ACT_MISH, true>()) return rc;
@@ -181,6 +185,10 @@ int gemm_run(const GemmPlan& pl, cudaStream_t s) {
   F5_GEMM_CASE(256, 3, EPI_F32, ACT_NONE, false)
   F5_GEMM_CASE(256, 3, EPI_RESID, ACT_NONE, false)
   F5_GEMM_CASE(128, 5, EPI_QKV_ROPE, ACT_NONE, false)
+  F5_GEMM_CASE(192, 4, EPI_QKV_ROPE, ACT_NONE, false)
+  F5_GEMM_CASE(192, 4, EPI_F16, ACT_NONE, false)
+  F5_GEMM_CASE(192, 4, EPI_F16, ACT_GELU_TANH, false)
+  F5_GEMM_CASE(192, 4, EPI_RESID, ACT_NONE, false)
   F5_GEMM_CASE(256, 3, EPI_QKV_ROPE, ACT_NONE, false)
   F5_GEMM_CASE(64, 7, EPI_F16, ACT_MISH, true)
   F5_GEMM_CASE(64, 7, EPI_RESID, ACT_MISH, true)
@@ -196,14 +204,67 @@ int gemm_run(const GemmPlan& pl, cudaStream_t s) {
   return -6;
 }
 
+struct TileChoice {
+  int bn, pair;
+};
+// Tile shape of a GEMM whose caller left bn = 0.  Cost model in SM clocks, fitted to the graph-timed sweep of
+// tools/gemm_sweep.py on B200 (profiles/README.md), all five tile flavours within ~5 %:
+//   main loop per tile  = k-blocks x (256 + 2*BN)     single CTA 128 x BN   (shared-memory traffic bound: TMA writes +
+//                         k-blocks x {474 | 640}      per CTA of a cta_group::2 256 x {128 | 256} pair (+1500 fixed)
+//   epilogue per tile   = BN x {27 plain fp16 / RoPE, 32 fp32 reduce-add, 38 GELU (two warps per scheduler)} clk
+//   tiles run in rounds over the SMs (SM pairs); inside a CTA the epilogue of tile i overlaps the main loop of tile
+//   i+1, so a round costs max(main, epilogue) and the last tile's epilogue is exposed.
+// F5_BN_<n_out>=<bn>[p] overrides the choice (experiments).
+TileChoice pick_tile(long long rows, int batches, int n_out, int k, int epi, int act) {
+  char key[32];
+  snprintf(key, sizeof key, "F5_BN_%d", n_out);
+  if (const char* e = getenv(key)) {
+    const int bn = atoi(e);
+    if (bn == 64 || bn == 128 || bn == 192 || bn == 256) return {bn, strchr(e, 'p') != nullptr ? 1 : 0};
+  }
+  const int sms = num_sms();
+  const double kb = double((k + 63) / 64);
+  const double epi_col = (act == F5_ACT_GELU_TANH || act == F5_ACT_GELU_ERF) ? 38.0 : (epi == F5_EPI_RESID ? 32.0 : 27.0);
+  // instantiated combinations only (configure_kernels)
+  const bool plain = act == F5_ACT_NONE, gelu = epi == F5_EPI_F16 && act == F5_ACT_GELU_TANH;
+  const bool wide_ok = (epi == F5_EPI_F16 && (plain || gelu)) || ((epi == F5_EPI_RESID || epi == F5_EPI_QKV_ROPE) && plain);
+  TileChoice best{128, 0};
+  double best_cost = 1e30;
+  const int cand[5][2] = {{128, 0}, {192, 0}, {256, 0}, {128, 1}, {256, 1}};
+  for (const auto& c : cand) {
+    const int bn = c[0], pair = c[1];
+    if ((pair || bn == 192) && !wide_ok) continue;
+    if (bn > 128 && n_out < bn) continue;
+    if (pair && n_out < 256) continue;
+    const long long tm = pair ? (rows + 255) / 256 : (rows + 127) / 128;
+    const long long tiles = tm * ((n_out + bn - 1) / bn) * batches;
+    const long long units = pair ? sms / 2 : sms;
+    const double rounds = double((tiles + units - 1) / units);
+    const double main_clk = kb * (pair ? (bn == 256 ? 640.0 : 474.0) : 256.0 + 2.0 * bn);
+    const double epi_clk = epi_col * bn;               // exposed (last tile): latency-bound, one warp per scheduler
+    const double epi_pace = epi_clk * (50.0 / 60.0);  // overlapped with the next main loop it runs a little faster
+    const double cost = (rounds - 1.0) * (main_clk > epi_pace ? main_clk : epi_pace) + main_clk + epi_clk + (pair ? 1500.0 /*cluster sync, remote barrier hops*/ : 0.0);
+    if (cost < best_cost) {
+      best_cost = cost;
+      best = {bn, pair};
+    }
+  }
+  return best;
+}
+
 int gemm_plan(GemmPlan* pl, const void* A, const void* W, const f5_gemm_args* a) {
   memset(pl, 0, sizeof(*pl));
   const bool conv = a->conv_taps > 0;
   int bn = a->bn;
+  int want_pair = a->cta_pair;
   if (conv) bn = 64;
-  if (bn == 0) bn = 128;
-  if (bn != 64 && bn != 128 && bn != 256) {
-    set_error("gemm: bn must be 64, 128 or 256");
+  if (bn == 0) {  // caller leaves the tile shape to the planner
+    const TileChoice tc = pick_tile(a->rows, a->batches, a->n_out, a->k, a->epi, a->act);
+    bn = tc.bn;
+    want_pair = tc.pair;
+  }
+  if (bn != 64 && bn != 128 && bn != 192 && bn != 256) {
+    set_error("gemm: bn must be 64, 128, 192 or 256");
     return -1;
   }
   if (a->rows <= 0 || a->batches <= 0 || a->n_out <= 0) {
@@ -218,7 +279,7 @@ int gemm_plan(GemmPlan* pl, const void* A, const void* W, const f5_gemm_args* a)
   pl->epi = a->epi;
   pl->act = a->act;
   pl->conv = conv ? 1 : 0;
-  pl->pair = (!conv && a->cta_pair && a->epi != F5_EPI_F32 && (bn == 128 || bn == 256)) ? 1 : 0;
+  pl->pair = (!conv && want_pair && a->epi != F5_EPI_F32 && (bn == 128 || bn == 256)) ? 1 : 0;
   GemmParams& p = pl->p;
   p.rows = a->rows;
   p.n_out = a->n_out;
@@ -324,6 +385,19 @@ int f5_debug_gemm_trace(long long* host_out, int n_ctas) {
   if (!f5::g_trace) return -1;
   cudaDeviceSynchronize();
   return cudaMemcpy(host_out, f5::g_trace, sizeof(long long) * 16 * (size_t)n_ctas, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -2;
+}
+
+int f5_gemm_tile(const f5_gemm_args* args, int* bn, int* cta_pair) {
+  if (!args || !bn || !cta_pair) return -1;
+  int b = args->conv_taps > 0 ? 64 : args->bn, pr = args->cta_pair;
+  if (b == 0) {
+    const f5::TileChoice tc = f5::pick_tile(args->rows, args->batches, args->n_out, args->k, args->epi, args->act);
+    b = tc.bn;
+    pr = tc.pair;
+  }
+  *bn = b;
+  *cta_pair = (args->conv_taps == 0 && pr && args->epi != F5_EPI_F32 && (b == 128 || b == 256)) ? 1 : 0;
+  return 0;
 }
 
 int f5_gemm(const void* A, const void* W, const f5_gemm_args* args, f5_stream_t stream) {

@@ -3,15 +3,16 @@
 //   C[m, n] = epilogue( sum_k A[m, k] * W[n, k] )        A, W fp16, K-major; fp32 accumulation in TMEM.
 //
 // grid = min(#tiles, #SMs); every CTA walks tiles t = blockIdx.x, +gridDim.x, ... (n fastest, so CTAs that run
-// together share the A row-panel in L2 and sweep W once).  Warp roles (192 threads):
+// together share the A row-panel in L2 and sweep W once).  Warp roles (320 threads):
 //   warp 0        TMA producer (one elected lane): STAGES-deep ring of {A 128x64, W BNx64} fp16 tiles, SWIZZLE_128B
 //   warp 1        TMEM allocator + single-thread tcgen05.mma issuer; accumulators double-buffered in TMEM
 //                 (2 x BN columns) so the epilogue of tile i overlaps the main loop of tile i+1
-//   warps 2..5    epilogue: tcgen05.ld (one accumulator row per thread) -> fused bias / activation / RoPE / gate /
-//                 mask -> 128-byte row chunks staged in shared memory (128B swizzle, conflict free) -> ONE elected
-//                 thread issues a bulk TMA store (fp16 outputs) or a TMA reduce-add (fp32 residual: x += ..., the
-//                 residual is never read by the SM).  Per-thread scattered global stores were measured 2.4x slower
-//                 than the whole main loop.  Warp w owns TMEM lane quarter (w % 4).
+//   warps 2..9    epilogue, two column groups of four warps: tcgen05.ld (one accumulator row per thread) -> fused bias /
+//                 activation / RoPE / gate / mask -> 128-byte row chunks staged in shared memory (128B swizzle, conflict
+//                 free) -> ONE elected thread per group issues a bulk TMA store (fp16 outputs) or a TMA reduce-add (fp32
+//                 residual: x += ..., the residual is never read by the SM).  Per-thread scattered global stores were
+//                 measured 2.4x slower than the whole main loop.  Warp w owns TMEM lane quarter (w % 4); the second
+//                 warp per quarter exists because ONE epilogue warp per scheduler is latency-bound.
 // Pipelines: smem full/empty mbarriers (TMA <-> MMA), TMEM acc_full/acc_empty mbarriers (MMA <-> epilogue).
 // Tails in M, N and K come from TMA out-of-bounds zero fill plus guarded stores.
 //
@@ -26,7 +27,14 @@
 namespace f5 {
 
 constexpr uint32_t kEpiChunkBytes = kBM * 128;  // 128 rows x 128 B (64 fp16 or 32 fp32 columns)
-constexpr int kEpiBufs = 3;                     // staging ring: a bulk store may queue behind operand loads in the TMA unit
+constexpr int kEpiBufs = 2;                     // one staging buffer per epilogue column group
+
+// Epilogue warps per TMEM lane quarter.  ONE warp per scheduler is latency-bound, so activation epilogues (GELU / Mish:
+// ~2x the instructions) get a second column group (measured FF1: 14.1 -> 12.4 us at M = 1876, 1025 -> 1196 TFLOP/s at
+// M = 15008); the plain / RoPE / reduce-add epilogues were not faster with eight warps (register cap 168, single TMEM
+// buffer) and keep four.
+__host__ __device__ constexpr int gemm_epi_groups(int act) { return act != ACT_NONE ? 2 : 1; }
+__host__ __device__ constexpr int gemm_threads(int act) { return 64 + 128 * gemm_epi_groups(act); }
 
 template <int BN, int STAGES, bool PAIR = false>
 constexpr size_t gemm_smem_bytes() {
@@ -210,7 +218,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
 // each CTA's accumulator half lands in its own TMEM.  Shared-memory traffic per MMA cycle drops by 1/4 (BN = 256) —
 // the measured limiter of the single-CTA kernel (operand writes by TMA + reads by the tensor core > 128 B/clk).
 template <int BN, int STAGES, int EPI, int ACT, bool CONV, bool PAIR = false>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(gemm_threads(ACT), 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
   static_assert(!(PAIR && CONV), "the conv schedule is single-CTA");
@@ -218,8 +226,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   constexpr int TM = PAIR ? 2 * kBM : kBM;  // rows of one (pair-)tile
   constexpr uint32_t A_BYTES = kBM * kBK * 2;
   constexpr uint32_t B_BYTES = BNL * kBK * 2;
-  constexpr uint32_t TMEM_COLS = 2 * BN;  // double-buffered accumulator (power of two: 128 / 256 / 512)
-  static_assert(BN == 64 || BN == 128 || BN == 256, "BN");
+  constexpr uint32_t TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;  // double-buffered accumulator
+  static_assert(BN == 64 || BN == 128 || BN == 192 || BN == 256, "BN");
+  static_assert(!(PAIR && BN == 192), "pair tiles are 128 or 256 wide");
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -264,7 +273,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&acc_full[b], 1);
-      mbar_init(&acc_empty[b], PAIR ? 256 : 128);  // PAIR: both CTAs' epilogue threads arrive on the leader's barrier
+      mbar_init(&acc_empty[b], (PAIR ? 2 : 1) * 128 * gemm_epi_groups(ACT));  // PAIR: both CTAs' epilogue threads arrive on the leader's barrier
     }
     fence_mbar_init();
   }
@@ -277,8 +286,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  pdl_wait();               // predecessor kernel finished: its outputs (our operands) are visible
-  pdl_launch_dependents();  // let the next kernel's prologue overlap our tail
+  // Programmatic dependent launch: everything above overlapped the predecessor's tail.  The producer thread goes one
+  // step further (below): W tiles are weights, not produced by the predecessor, so their TMA loads are issued BEFORE
+  // the dependency wait and the DRAM latency of the first STAGES k-blocks hides under the predecessor too.
+  if (warp != 0) pdl_wait();  // predecessor kernel finished: its outputs (our A operand, residual, ...) are visible
+  pdl_launch_dependents();    // let the next kernel's prologue overlap our tail
 #ifdef F5_TRACE
   if (ts && threadIdx.x == 0) ts[2] = clock64();  // setup done
 #endif
@@ -287,6 +299,30 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (elect_one()) {
       // ===== TMA producer =====
       uint32_t it = 0;  // running k-block counter across tiles -> stage / phase
+      // W tile of k-block kb of the tile at column n0 -> stage s (barrier already armed)
+      auto load_w = [&](int s, int kb, int n0) {
+        if (PAIR) tma_load_2d_pair(sB + s * B_BYTES, &tmB, mapa_u32(&full[s], 0), kb * kBK, n0 + int(rank) * BNL);
+        else if (CONV) tma_load_2d(sB + s * B_BYTES, &tmB, &full[s], 0, kb * p.n_out + n0);  // [tap][out_channel][in 64]
+        else tma_load_2d(sB + s * B_BYTES, &tmB, &full[s], kb * kBK, n0);
+      };
+      auto arm = [&](int s) {
+        // PAIR: both CTAs load; every byte is credited to the LEADER's full barrier, which the MMA issuer waits on
+        if (PAIR) {
+          if (rank == 0) mbar_expect_tx(&full[s], 2 * (A_BYTES + B_BYTES));
+        } else {
+          mbar_expect_tx(&full[s], A_BYTES + B_BYTES);
+        }
+      };
+      // weights of the first tile's first k-blocks: in flight before the dependency wait (slots are free at start)
+      uint32_t pre = 0;
+      if (cta_id < num_tiles && p.dbg_mode != 1) {
+        pre = uint32_t(p.num_kb < STAGES ? p.num_kb : STAGES);
+        for (uint32_t kb = 0; kb < pre; ++kb) {
+          arm(int(kb));
+          load_w(int(kb), int(kb), (cta_id % tiles_n) * BN);
+        }
+      }
+      pdl_wait();
       for (int t = cta_id; t < num_tiles; t += cta_step) {
         const int n0 = (t % tiles_n) * BN;
         const int m0 = ((t / tiles_n) % tiles_m) * TM + int(rank) * kBM;
@@ -294,29 +330,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
-          mbar_wait(&empty[s], ph ^ 1);
-          if (p.dbg_mode == 1) {
-            mbar_arrive(&full[s]);
-            continue;
+          if (it >= pre) {
+            mbar_wait(&empty[s], ph ^ 1);
+            if (p.dbg_mode == 1) {
+              mbar_arrive(&full[s]);
+              continue;
+            }
+            arm(s);
+            load_w(s, kb, n0);
           }
-          if (PAIR) {
-            // both CTAs load; every byte is credited to the LEADER's full barrier, which the MMA issuer waits on
-            if (rank == 0) mbar_expect_tx(&full[s], 2 * (A_BYTES + B_BYTES));
-            const uint32_t lbar = mapa_u32(&full[s], 0);
-            tma_load_3d_pair(sA + s * A_BYTES, &tmA, lbar, kb * kBK, m0, bz);
-            tma_load_2d_pair(sB + s * B_BYTES, &tmB, lbar, kb * kBK, n0 + int(rank) * BNL);
-            continue;
-          }
-          mbar_expect_tx(&full[s], A_BYTES + B_BYTES);
-          if (CONV) {
-            // A: activation [batch][seq][channels]; group = n-tile (BN == 64 == channels per group)
-            tma_load_3d(sA + s * A_BYTES, &tmA, &full[s], n0, m0 + kb - p.conv_pad, bz);
-            // W repacked [tap][out_channel][in 64]: rows = tap * n_out + out_channel
-            tma_load_2d(sB + s * B_BYTES, &tmB, &full[s], 0, kb * p.n_out + n0);
-          } else {
-            tma_load_3d(sA + s * A_BYTES, &tmA, &full[s], kb * kBK, m0, bz);
-            tma_load_2d(sB + s * B_BYTES, &tmB, &full[s], kb * kBK, n0);
-          }
+          if (PAIR) tma_load_3d_pair(sA + s * A_BYTES, &tmA, mapa_u32(&full[s], 0), kb * kBK, m0, bz);
+          else if (CONV) tma_load_3d(sA + s * A_BYTES, &tmA, &full[s], n0, m0 + kb - p.conv_pad, bz);  // tap shift
+          else tma_load_3d(sA + s * A_BYTES, &tmA, &full[s], kb * kBK, m0, bz);
         }
       }
     }
@@ -358,12 +383,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #endif
     }
   } else {
-    // ===== epilogue: warps 2..5 -> TMEM lane quarters 2,3,0,1 =====
+    // ===== epilogue: warps 2.. (4 * EG warps).  Warp w reads TMEM lane quarter w % 4 (rows); with EG = 2 column group
+    // eg = (w - 2) / 4 takes every other 128-byte chunk of the tile, so two warps per scheduler hide each other's
+    // latencies (a lone warp needs ~860 clk per 32-column piece for ~200 issue slots).
+    constexpr int EG = gemm_epi_groups(ACT);
+    constexpr int ETH = 128 * EG;  // epilogue threads
     const int q = warp & 3;
+    const int eg = (EG == 2) ? (warp - 2) >> 2 : 0;
+    const int et = int(threadIdx.x) - 64;                 // 0 .. ETH-1
+    const bool issuer = (et == eg * 128);                 // owns this group's bulk stores
+    const int bar_a = 1 + 2 * eg, bar_b = 2 + 2 * eg;     // named barriers of this column group (128 threads)
+    uint8_t* sbuf = sC + eg * kEpiChunkBytes;             // one staging buffer per group (values wait in registers)
     const float* gate = nullptr;
     if (EPI == EPI_RESID && p.gate != nullptr)
       gate = p.gate + (p.step_ptr ? (long long)(*p.step_ptr) : 0) * p.gate_step_stride;
-    uint32_t tl = 0, chunk_ctr = 0;
+    uint32_t tl = 0;
 #ifdef F5_TRACE
     long long t_accwait = 0;
 #endif
@@ -384,10 +418,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       // ---- prefetch everything the epilogue reads from global memory while the main loop of this tile runs ----
       float4 rope_c[8], rope_s[8];
       if (EPI != EPI_F32) {
-        named_bar_sync(3, 128);  // every thread is done with the previous tile's sBias / sGate
-        const int et = threadIdx.x - 64;
+        named_bar_sync(5, ETH);  // every thread is done with the previous tile's sBias / sGate
 #pragma unroll
-        for (int c = et; c < BN; c += 128) {
+        for (int c = et; c < BN; c += ETH) {
           const int n = n0 + c;
           sBias[c] = (p.bias != nullptr && n < p.n_out) ? __ldg(p.bias + n) : 0.0f;
           if (EPI == EPI_RESID) sGate[c] = (gate != nullptr && n < p.n_out) ? __ldg(gate + n) : 1.0f;
@@ -420,7 +453,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (EPI == EPI_F32) {
         // direct stores (used once per step for the input projection: fp32 + masked fp16 copy)
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = eg; c < BN / 32; c += EG) {
           uint32_t r[32];
           tmem_ld32(tmem_acc + uint32_t(c * 32), r);
           tmem_ld_wait();
@@ -429,88 +462,93 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
       } else {
         // staged: 32-column pieces -> 128-byte row chunks in swizzled smem -> bulk TMA store / reduce-add.
-        // All global reads the epilogue needs (bias, gate, rotary rows) are issued BEFORE the accumulator wait (see
-        // below) and TMEM loads are double-buffered, so no DRAM/L2/TMEM latency sits on the per-chunk path.
+        // All global reads the epilogue needs (bias, gate, rotary rows) were issued BEFORE the accumulator wait, TMEM
+        // loads are double-buffered, and a chunk's values wait in registers until the group's staging buffer has been
+        // read by the previous bulk store, so no DRAM / L2 / TMEM / TMA latency sits on the per-chunk path.
         constexpr int PIECES = BN / 32;
         constexpr int PPC = (EPI == EPI_RESID) ? 1 : 2;  // pieces per 128-byte chunk
+        constexpr int NCH = PIECES / PPC;                // chunks per tile
+        constexpr int NCHG = (NCH + EG - 1) / EG;        // chunks per column group (upper bound)
+        constexpr bool DB = true;                        // TMEM loads double-buffered
+        named_bar_sync(6, ETH);                          // sBias / sGate of this tile are published
         const int erow = q * 32 + int(lane_id());
-        const bool issuer = (threadIdx.x == 64);
         uint32_t ra[32], rb[32];
-        tmem_ld32(tmem_acc, ra);
+        if (eg < NCH) tmem_ld32(tmem_acc + uint32_t(eg * PPC * 32), ra);
 #pragma unroll
-        for (int pc = 0; pc < PIECES; ++pc) {
-          uint32_t(&rc)[32] = (pc & 1) ? rb : ra;
-          uint32_t(&rn)[32] = (pc & 1) ? ra : rb;
-          tmem_ld_wait();
-          if (pc + 1 < PIECES) tmem_ld32(tmem_acc + uint32_t((pc + 1) * 32), rn);
-          const int ch = pc / PPC, sub = pc % PPC;
-          uint8_t* sbuf = sC + ((chunk_ctr + ch) % kEpiBufs) * kEpiChunkBytes;
-          if (sub == 0) {
-            if (issuer) tma_store_wait_read<kEpiBufs - 1>();  // the store that last used this buffer drained it
-            named_bar_sync(1, 128);                           // (also publishes sBias / sGate of this tile)
-          }
-          const int ct = pc * 32;  // column inside the tile
-          float v[32];
+        for (int i = 0; i < NCHG; ++i) {
+          const int ch = eg + EG * i;
+          if (ch < NCH) {
+            uint32_t st[32];  // RESID: 32 fp32 values ; fp16: 2 x 16 packed pairs
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float4 b = *reinterpret_cast<const float4*>(sBias + ct + 4 * i);
-            v[4 * i + 0] = __uint_as_float(rc[4 * i + 0]) + b.x;
-            v[4 * i + 1] = __uint_as_float(rc[4 * i + 1]) + b.y;
-            v[4 * i + 2] = __uint_as_float(rc[4 * i + 2]) + b.z;
-            v[4 * i + 3] = __uint_as_float(rc[4 * i + 3]) + b.w;
-          }
-          if (EPI == EPI_QKV_ROPE) {
-            const int nc = n0 + ct;
-            const int sec = nc / p.inner, head = (nc % p.inner) / 64;
-            if (sec < 2 && head < p.pe_heads) {
-              // pairs 0..15 of the head for its first 32 columns, pairs 16..31 for the second
+            for (int sub = 0; sub < PPC; ++sub) {
+              const int k = i * PPC + sub;  // running piece counter of this group (compile time)
+              uint32_t(&rc)[32] = (DB && (k & 1)) ? rb : ra;
+              uint32_t(&rn)[32] = (DB && !(k & 1)) ? rb : ra;
+              const int pc = ch * PPC + sub;
+              const int pc_next = (sub + 1 < PPC) ? pc + 1 : (ch + EG) * PPC;
+              const bool has_next = (sub + 1 < PPC) || (ch + EG < NCH);
+              tmem_ld_wait();
+              if (DB && has_next) tmem_ld32(tmem_acc + uint32_t(pc_next * 32), rn);
+              const int ct = pc * 32;  // column inside the tile
+              float v[32];
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float4 c4 = rope_c[(nc % 64) ? 4 + i : i], s4 = rope_s[(nc % 64) ? 4 + i : i];
-                const float cc[4] = {c4.x, c4.y, c4.z, c4.w}, ss[4] = {s4.x, s4.y, s4.z, s4.w};
+              for (int j = 0; j < 8; ++j) {
+                const float4 bb = *reinterpret_cast<const float4*>(sBias + ct + 4 * j);
+                v[4 * j + 0] = __uint_as_float(rc[4 * j + 0]) + bb.x;
+                v[4 * j + 1] = __uint_as_float(rc[4 * j + 1]) + bb.y;
+                v[4 * j + 2] = __uint_as_float(rc[4 * j + 2]) + bb.z;
+                v[4 * j + 3] = __uint_as_float(rc[4 * j + 3]) + bb.w;
+              }
+              if (!DB && has_next) tmem_ld32(tmem_acc + uint32_t(pc_next * 32), ra);  // rc == ra has been consumed into v
+              if (EPI == EPI_QKV_ROPE) {
+                const int nc = n0 + ct;
+                const int sec = nc / p.inner, head = (nc % p.inner) / 64;
+                if (sec < 2 && head < p.pe_heads) {
+                  // pairs 0..15 of the head for its first 32 columns, pairs 16..31 for the second
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const float x0 = v[8 * i + 2 * j], x1 = v[8 * i + 2 * j + 1];
-                  v[8 * i + 2 * j] = x0 * cc[j] - x1 * ss[j];
-                  v[8 * i + 2 * j + 1] = x1 * cc[j] + x0 * ss[j];
+                  for (int j = 0; j < 4; ++j) {
+                    const float4 c4 = rope_c[(nc % 64) ? 4 + j : j], s4 = rope_s[(nc % 64) ? 4 + j : j];
+                    const float cc[4] = {c4.x, c4.y, c4.z, c4.w}, ss[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                      const float x0 = v[8 * j + 2 * u], x1 = v[8 * j + 2 * u + 1];
+                      v[8 * j + 2 * u] = x0 * cc[u] - x1 * ss[u];
+                      v[8 * j + 2 * u + 1] = x1 * cc[u] + x0 * ss[u];
+                    }
+                  }
                 }
               }
-            }
-          }
-          if (ACT != ACT_NONE) {
+              if (ACT != ACT_NONE) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              if (ACT == ACT_GELU_TANH) v[i] = gelu_tanh(v[i]);
-              if (ACT == ACT_GELU_ERF) v[i] = gelu_erf(v[i]);
-              if (ACT == ACT_MISH) v[i] = mish(v[i]);
-            }
-          }
-          uint8_t* srow = sbuf + erow * 128;
-          if (EPI == EPI_RESID) {
+                for (int j = 0; j < 32; ++j) {
+                  if (ACT == ACT_GELU_TANH) v[j] = gelu_tanh(v[j]);
+                  if (ACT == ACT_GELU_ERF) v[j] = gelu_erf(v[j]);
+                  if (ACT == ACT_MISH) v[j] = mish(v[j]);
+                }
+              }
+              if (EPI == EPI_RESID) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float4 g = *reinterpret_cast<const float4*>(sGate + ct + 4 * i);
-              float4 o;
-              o.x = valid ? g.x * v[4 * i] : 0.f;
-              o.y = valid ? g.y * v[4 * i + 1] : 0.f;
-              o.z = valid ? g.z * v[4 * i + 2] : 0.f;
-              o.w = valid ? g.w * v[4 * i + 3] : 0.f;
-              *reinterpret_cast<float4*>(srow + ((i ^ (erow & 7)) << 4)) = o;
-            }
-          } else {
+                for (int j = 0; j < 8; ++j) {
+                  const float4 g = *reinterpret_cast<const float4*>(sGate + ct + 4 * j);
+                  st[4 * j + 0] = __float_as_uint(valid ? g.x * v[4 * j] : 0.f);
+                  st[4 * j + 1] = __float_as_uint(valid ? g.y * v[4 * j + 1] : 0.f);
+                  st[4 * j + 2] = __float_as_uint(valid ? g.z * v[4 * j + 2] : 0.f);
+                  st[4 * j + 3] = __float_as_uint(valid ? g.w * v[4 * j + 3] : 0.f);
+                }
+              } else {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              uint4 w;
-              w.x = valid ? pack_half2(v[8 * i + 0], v[8 * i + 1]) : 0u;
-              w.y = valid ? pack_half2(v[8 * i + 2], v[8 * i + 3]) : 0u;
-              w.z = valid ? pack_half2(v[8 * i + 4], v[8 * i + 5]) : 0u;
-              w.w = valid ? pack_half2(v[8 * i + 6], v[8 * i + 7]) : 0u;
-              *reinterpret_cast<uint4*>(srow + (((sub * 4 + i) ^ (erow & 7)) << 4)) = w;
+                for (int j = 0; j < 16; ++j) st[sub * 16 + j] = valid ? pack_half2(v[2 * j], v[2 * j + 1]) : 0u;
+              }
             }
-          }
-          if (sub == PPC - 1) {
+            if (issuer) tma_store_wait_read<0>();  // the group's previous bulk store has read the staging buffer
+            named_bar_sync(bar_a, 128);
+            uint8_t* srow = sbuf + erow * 128;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<uint4*>(srow + ((j ^ (erow & 7)) << 4)) =
+                  make_uint4(st[4 * j], st[4 * j + 1], st[4 * j + 2], st[4 * j + 3]);
             fence_proxy_async_smem();
-            named_bar_sync(2, 128);
+            named_bar_sync(bar_b, 128);
             if (issuer && p.dbg_mode != 3) {
               const int c0 = n0 + ch * (32 * PPC);
               if (c0 < p.n_out) {
@@ -521,7 +559,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
           }
         }
-        chunk_ctr += PIECES / PPC;
       }
       tc_fence_before();
       if (PAIR) mbar_arrive_cluster(mapa_u32(&acc_empty[buf], 0));  // the leader's MMA issuer owns the accumulator ring
@@ -530,7 +567,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #ifdef F5_TRACE
     if (ts && threadIdx.x == 64) ts[12] = clock64();
 #endif
-    if (EPI != EPI_F32 && threadIdx.x == 64) tma_store_wait_read<0>();  // smem must outlive the last bulk store
+    if (EPI != EPI_F32 && issuer) {
+      tma_store_wait_read<0>();  // smem must outlive the last bulk store
+    }
 #ifdef F5_TRACE
     if (ts && threadIdx.x == 64) {
       ts[6] = clock64();  // epilogue done

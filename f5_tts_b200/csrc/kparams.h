@@ -38,7 +38,6 @@ struct GemmParams {
   int dbg_mode;  // 0 normal; 1 = skip TMA loads, 2 = skip MMAs, 3 = skip epilogue math/stores (perf decomposition only)
 };
 
-constexpr int kGemmThreads = 192;
 constexpr int kBM = 128;
 constexpr int kBK = 64;
 
@@ -52,7 +51,6 @@ struct AttnParams {
   float scale_log2;   // softmax scale * log2(e)
   __half* out;        // [Be*seq, inner]
   long long* dbg_ts;  // optional [CTAs][16] phase-cycle trace (diagnostics; NULL in production)
-  int variant;        // 3: one thread per query row (320 threads); 4: two threads per row (576 threads)
   int turnstile;      // 1: serialise the exp2 loops of the two softmax warpgroups (ping-pong); 0: free-running
 };
 
@@ -63,6 +61,5 @@ constexpr int kAttnStages = 3;      // K and V rings
 constexpr uint32_t kAttnTile = 128 * 64 * 2;  // 16 KB
 // Q x2 + K,V rings + P (2 warpgroups x 2 sub-tiles) + alignment slack + barriers
 constexpr size_t kAttnSmem = size_t(kAttnTile) * (2 + 2 * kAttnStages + 4) + 1024 + 256 + 4096;  // + row-stat exchange (v4)
-constexpr int kAttn4Threads = 64 + 512;  // v4: TMA warp + MMA warp + 16 softmax warps (two threads per query row)
 
 }  // namespace f5

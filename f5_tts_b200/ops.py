@@ -66,6 +66,15 @@ def linear(a: torch.Tensor, w: torch.Tensor, bias=None, *, epi=EPI_F16, act=ACT_
     return (out, out2) if out16b else out
 
 
+def gemm_tile(M: int, N: int, K: int, epi=EPI_F16, act=ACT_NONE, bn=0, pair=0):
+    """(tile width, cta_pair) the planner runs this GEMM shape with."""
+    g = _lib.GemmArgs()
+    g.rows, g.batches, g.n_out, g.k, g.bn, g.epi, g.act, g.cta_pair = M, 1, N, K, bn, epi, act, pair
+    b, pr = C.c_int(0), C.c_int(0)
+    _lib.check(_lib.lib().f5_gemm_tile(C.byref(g), C.byref(b), C.byref(pr)), "f5_gemm_tile")
+    return b.value, pr.value
+
+
 def grouped_conv31(x: torch.Tensor, w_packed: torch.Tensor, bias, *, resid=None, row_len=None):
     """Conv1d(k=31, groups=D/64, pad=15) + bias + (mask) + Mish over x fp16 [B, N, D]; w_packed fp16 [31, D, 64].
     resid given: resid += result (fp32, in place) else returns fp16 [B, N, D]."""

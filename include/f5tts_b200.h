@@ -51,7 +51,7 @@ typedef struct {
   int n_out;
   int k;         /* reduction length (plain) ; ignored for conv */
   int lda, ldw;  /* elements */
-  int bn;        /* output tile width: 64 | 128 | 256 (0 = pick) */
+  int bn;        /* output tile width: 64 | 128 | 192 | 256 (0 = the planner picks width and cta_pair) */
   int epi, act;
   int conv_taps; /* 0 = plain GEMM */
   int cta_pair;  /* 1 = 2-CTA (cta_group::2) 256 x bn tiles; bn must be 128 or 256; plain GEMM, not EPI_F32 */
@@ -70,6 +70,8 @@ typedef struct {
   int inner, pe_heads;
 } f5_gemm_args;
 int f5_gemm(const void* A, const void* W, const f5_gemm_args* args, f5_stream_t stream);
+/* Tile shape f5_gemm would run `args` with (after bn = 0 resolution): *bn tile width, *cta_pair 0/1. */
+int f5_gemm_tile(const f5_gemm_args* args, int* bn, int* cta_pair);
 
 /* Non-causal attention over the fused QKV buffer — replaces F.scaled_dot_product_attention at
  * model/modules.py:519 (attn_mask=None, or the key mask of modules.py:513-517 via kv_len).

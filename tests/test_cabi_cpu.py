@@ -68,3 +68,22 @@ def test_text_helpers():
     assert infer.chunk_text("A b. C d! E", 5) == ["A b.", "C d!", "E"]
     toks = infer.convert_char_to_pinyin(["Hi there; ok"])[0]
     assert "".join(toks) == "Hi there, ok"
+
+
+def test_gemm_tile_planner():
+    """bn = 0 leaves the tile shape to the planner; the query entry point reports what f5_gemm will run (host logic only)."""
+    from f5_tts_b200 import _lib, ops
+    from f5_tts_b200.ops import ACT_GELU_ERF, ACT_NONE, EPI_F16, EPI_F32, EPI_QKV_ROPE, EPI_RESID
+
+    if not os.path.exists(_lib.LIB_PATH):
+        pytest.skip("library not built (run __graft_entry__.build())")
+    for M, N, K, epi, act in ((1876, 3072, 1024, EPI_QKV_ROPE, ACT_NONE), (1876, 1024, 2048, EPI_RESID, ACT_NONE),
+                              (15008, 3072, 1024, EPI_QKV_ROPE, ACT_NONE), (300, 100, 1024, EPI_F32, ACT_NONE),
+                              (700, 1024, 512, EPI_F16, ACT_GELU_ERF)):
+        bn, pair = ops.gemm_tile(M, N, K, epi, act)
+        assert bn in (64, 128, 192, 256) and pair in (0, 1)
+        assert not (pair and epi == EPI_F32)
+        if act == ACT_GELU_ERF:
+            assert bn != 192 and not pair  # only instantiated shapes are ever chosen
+    assert ops.gemm_tile(1876, 1024, 1024, EPI_RESID, ACT_NONE, bn=64) == (64, 0)  # explicit request is kept
+    assert ops.gemm_tile(15008, 3072, 1024, EPI_QKV_ROPE, ACT_NONE) == (256, 1)  # large batch: cta_group::2 pairs

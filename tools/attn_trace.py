@@ -24,5 +24,5 @@ for Be, seq, H in ((2, 938, 16), (16, 938, 16)):
     for w in (0, 1):
         o = w * 8
         print(f"Be={Be} seq={seq} WG{w} (median over {n} CTAs, us): wait S {np.median(t[:,o+0]):.2f} | turnstile {np.median(t[:,o+1]):.2f} | "
-              f"tmem ld {np.median(t[:,o+7]):.2f} | max+exp {np.median(t[:,o+2]):.2f} | wait O {np.median(t[:,o+3]):.2f} | write P+rescale+arrive {np.median(t[:,o+4]):.2f} | "
-              f"total loop {np.median(t[:,o+5]):.2f} | kv tiles {np.median(buf[:,o+6])}", flush=True)
+              f"tmem ld {np.median(t[:,o+7]):.2f} | max {np.median(t[:,o+6]):.2f} | exp {np.median(t[:,o+2]):.2f} | wait O {np.median(t[:,o+3]):.2f} | write P+rescale+arrive {np.median(t[:,o+4]):.2f} | "
+              f"total loop {np.median(t[:,o+5]):.2f} | kv tiles {(seq + 127) // 128}", flush=True)
