@@ -34,6 +34,11 @@ __device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
 template <bool FULL>
 __device__ __forceinline__ void exp_pack32(const uint32_t (&r)[32], int col0, int kv_rem, float sc, float ms,
                                            float& sum_a, float& sum_b, uint32_t* pk) {
+  if (!FULL && col0 >= kv_rem) {  // warp-uniform: every key of this chunk is past the end of the sample -> P = 0, no MUFU
+#pragma unroll
+    for (int i = 0; i < 16; ++i) pk[i] = 0u;
+    return;
+  }
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
     float e0 = ex2_approx(__uint_as_float(r[2 * i]) * sc - ms);

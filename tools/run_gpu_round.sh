@@ -3,11 +3,8 @@
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv | tee gpurun_out/gpu.txt
 if [ "${SKIP_TESTS:-0}" != "1" ]; then
-for f in tests/test_gpu_kernels.py tests/test_gpu_sample.py; do
-  b=$(basename $f .py)
-  echo "=== $f"
-  timeout 900 python -m pytest $f -q -m gpu -s --tb=short 2>&1 | tail -${TAILN:-70} | tee gpurun_out/$b.log
-done
+  echo "=== pytest -m gpu (the driver's command, one process)"
+  timeout 1500 python -m pytest tests/ -x -q -m gpu 2>&1 | tail -${TAILN:-12} | tee gpurun_out/test_gpu.log
 fi
 echo "=== smoke"
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -5 | tee gpurun_out/smoke.log
