@@ -189,7 +189,7 @@ def isolated_gemm_roofline(M, seq, peaks, dev):
         if epi == ops.EPI_RESID:
             kw["resid"] = torch.zeros(M, N, device=dev)
             kw["gate"] = torch.randn(N, generator=g).to(dev)
-        us = _graph_time_us(lambda: [ops.linear(a[i % 2], w[i], b, epi=epi, act=act, bn=bn, pair=pair, **kw)
+        us = _graph_time_us(lambda: [ops.linear(a[i % 2], w[i], b, epi=epi, act=act, bn=bn, pair=pair, static_w=True, **kw)
                                      for i in range(n_w)], n_w)
         fl = 2.0 * M * N * K
         tile = ops.gemm_tile(M, N, K, epi, act)

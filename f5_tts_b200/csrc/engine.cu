@@ -233,6 +233,7 @@ struct StepPlans {
 
 f5_gemm_args base_args(long long rows, int n_out, int k, int lda, int ldw, int bn, int epi, int act) {
   f5_gemm_args a{};
+  a.weights_static = 1;  // every W the engine multiplies by is a packed model weight
   a.rows = (int)rows;
   a.batches = 1;
   a.n_out = n_out;
@@ -277,6 +278,7 @@ int build_step_plans(f5_engine* e, const Layout& L, const f5_sample_args* sa, St
   }
   for (int c = 0; c < 2; ++c) {  // grouped conv position embedding
     f5_gemm_args a{};
+    a.weights_static = 1;
     a.rows = L.N;
     a.batches = L.Be;
     a.n_out = D;

@@ -299,6 +299,7 @@ int gemm_plan(GemmPlan* pl, const void* A, const void* W, const f5_gemm_args* a)
   p.inner = a->inner > 0 ? a->inner : 64;
   p.pe_heads = a->pe_heads;
   p.conv_pad = a->conv_taps / 2;
+  p.w_prefetch = a->weights_static ? 1 : 0;
   {
     static int dbg = -1;
     if (dbg < 0) {

@@ -315,7 +315,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       };
       // weights of the first tile's first k-blocks: in flight before the dependency wait (slots are free at start)
       uint32_t pre = 0;
-      if (cta_id < num_tiles && p.dbg_mode != 1) {
+      if (cta_id < num_tiles && p.dbg_mode != 1 && p.w_prefetch) {
         pre = uint32_t(p.num_kb < STAGES ? p.num_kb : STAGES);
         for (uint32_t kb = 0; kb < pre; ++kb) {
           arm(int(kb));

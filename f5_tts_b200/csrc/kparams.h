@@ -34,6 +34,7 @@ struct GemmParams {
   int inner;     // heads * dim_head
   int pe_heads;  // heads that get rotary (q and k sections)
   int conv_pad;  // CONV: taps/2
+  int w_prefetch;  // W tiles may be loaded before griddepcontrol.wait (weights are not produced by the predecessor)
   long long* dbg_ts;  // optional [gridDim.x][8] clock64/globaltimer trace (diagnostics; NULL in production)
   int dbg_mode;  // 0 normal; 1 = skip TMA loads, 2 = skip MMAs, 3 = skip epilogue math/stores (perf decomposition only)
 };

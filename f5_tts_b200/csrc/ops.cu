@@ -204,6 +204,7 @@ int f5_vocos_decode(const f5_vocos_weights* w, const float* mel, int B, int T, v
   vocos_im2col_kernel<<<R, 256, 0, s>>>(mel, B, 100, T, A0, 704);
   count_launch();
   f5_gemm_args ga{};
+  ga.weights_static = 1;
   ga.rows = R; ga.batches = 1; ga.n_out = 512; ga.k = 704; ga.lda = 704; ga.ldw = 704; ga.bn = 64;
   ga.epi = F5_EPI_F32; ga.act = F5_ACT_NONE; ga.bias = w->embed_b; ga.out = e; ga.ldo = 512;
   if ((rc = f5_gemm(A0, w->embed_w, &ga, stream))) return rc;
@@ -217,10 +218,12 @@ int f5_vocos_decode(const f5_vocos_weights* w, const float* mel, int B, int T, v
     dp.ln_w = w->ln_w[i]; dp.ln_b = w->ln_b[i]; dp.eps = 1e-6f;
     if ((rc = run_dwconv7_ln(dp, s))) return rc;
     f5_gemm_args g1{};
+    g1.weights_static = 1;
     g1.rows = R; g1.batches = 1; g1.n_out = 1536; g1.k = 512; g1.lda = 512; g1.ldw = 512; g1.bn = 128;
     g1.epi = F5_EPI_F16; g1.act = F5_ACT_GELU_ERF; g1.bias = w->pw1_b[i]; g1.out = g; g1.ldo = 1536;
     if ((rc = f5_gemm(a, w->pw1_w[i], &g1, stream))) return rc;
     f5_gemm_args g2{};
+    g2.weights_static = 1;
     g2.rows = R; g2.batches = 1; g2.n_out = 512; g2.k = 1536; g2.lda = 1536; g2.ldw = 1536; g2.bn = 64;
     g2.epi = F5_EPI_RESID; g2.act = F5_ACT_NONE; g2.bias = w->pw2_b[i]; g2.resid = x; g2.ldo = 512;
     g2.gate = w->gamma[i];
@@ -232,6 +235,7 @@ int f5_vocos_decode(const f5_vocos_weights* w, const float* mel, int B, int T, v
     if ((rc = run_row_norm(1, np, s))) return rc;
   }
   f5_gemm_args gh{};
+  gh.weights_static = 1;
   gh.rows = R; gh.batches = 1; gh.n_out = 1026; gh.k = 512; gh.lda = 512; gh.ldw = 512; gh.bn = 128;
   gh.epi = F5_EPI_F32; gh.act = F5_ACT_NONE; gh.bias = w->head_b; gh.out = head; gh.ldo = 1026;
   if ((rc = f5_gemm(a, w->head_w, &gh, stream))) return rc;

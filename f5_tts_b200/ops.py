@@ -29,8 +29,9 @@ def _need_cuda(*ts):
 
 
 def linear(a: torch.Tensor, w: torch.Tensor, bias=None, *, epi=EPI_F16, act=ACT_NONE, bn=0, pair=0, resid=None, gate=None,
-           row_len=None, seq=0, rope=None, inner=0, pe_heads=0, out16b=False):
-    """C = epilogue(a @ w.T).  a fp16 [M, K], w fp16 [N, K] (both contiguous)."""
+           row_len=None, seq=0, rope=None, inner=0, pe_heads=0, out16b=False, static_w=False):
+    """C = epilogue(a @ w.T).  a fp16 [M, K], w fp16 [N, K] (both contiguous).
+    static_w: w is a model weight (not produced by the preceding kernel) -> its tiles may be prefetched early."""
     _need_cuda(a, w, bias, resid, gate)
     assert a.dtype == torch.float16 and w.dtype == torch.float16 and a.is_contiguous() and w.is_contiguous()
     M, K = a.shape
@@ -61,6 +62,7 @@ def linear(a: torch.Tensor, w: torch.Tensor, bias=None, *, epi=EPI_F16, act=ACT_
     if rope is not None:
         g.rope_cos, g.rope_sin = rope[0].data_ptr(), rope[1].data_ptr()
     g.inner, g.pe_heads = inner, pe_heads
+    g.weights_static = 1 if static_w else 0
     with torch.cuda.device(a.device):
         _lib.check(_lib.lib().f5_gemm(a.data_ptr(), w.data_ptr(), C.byref(g), _stream(a)), "f5_gemm")
     return (out, out2) if out16b else out
@@ -84,6 +86,7 @@ def grouped_conv31(x: torch.Tensor, w_packed: torch.Tensor, bias, *, resid=None,
     g.rows, g.batches, g.n_out, g.lda, g.conv_taps, g.act = N, B, D, D, 31, ACT_MISH
     g.bias = _ptr(bias)
     g.ldo, g.seq, g.row_len = D, N, _ptr(row_len)
+    g.weights_static = 1
     if resid is None:
         out = torch.empty((B, N, D), dtype=torch.float16, device=x.device)
         g.epi, g.out = EPI_F16, out.data_ptr()

@@ -68,6 +68,8 @@ typedef struct {
   const float* rope_cos;   /* [seq, 32] */
   const float* rope_sin;
   int inner, pe_heads;
+  int weights_static;      /* 1 = W was NOT written by the kernel preceding this call on the stream (model weights):
+                              its first tiles are fetched ahead of the programmatic-dependent-launch wait */
 } f5_gemm_args;
 int f5_gemm(const void* A, const void* W, const f5_gemm_args* args, f5_stream_t stream);
 /* Tile shape f5_gemm would run `args` with (after bn = 0 resolution): *bn tile width, *cta_pair 0/1. */

@@ -81,6 +81,8 @@ def test_gemm_f16_act(act, bn):
     a, w = gen((M, K), 4), gen((N, K), 5, 1 / math.sqrt(K))
     bias = gen((N,), 6, 0.5, torch.float32)
     out = ops.linear(a, w, bias, epi=EPI_F16, act=act, bn=bn)
+    # model weights may be fetched ahead of the programmatic-launch dependency wait: same bits either way
+    assert torch.equal(out, ops.linear(a, w, bias, epi=EPI_F16, act=act, bn=bn, static_w=True))
     ref = a.float() @ w.float().t() + bias
     if act == ACT_GELU_TANH:
         ref = F.gelu(ref, approximate="tanh")

@@ -18,7 +18,7 @@ def bench(M, N, K, epi, act, bn, nw=24, pair=0):
     a = [torch.randn(M, K, generator=g).half().to(DEV) for _ in range(2)]
     w = [(torch.randn(N, K, generator=g) / 32).half().to(DEV) for _ in range(nw)]
     b = torch.randn(N, generator=g).to(DEV)
-    kw = dict(epi=epi, act=act, bn=bn, pair=pair)
+    kw = dict(epi=epi, act=act, bn=bn, pair=pair, static_w=True)
     if epi == EPI_RESID:
         kw["resid"] = torch.zeros(M, N, device=DEV)
         kw["gate"] = torch.randn(N, generator=g).to(DEV)
