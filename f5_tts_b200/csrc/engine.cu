@@ -246,16 +246,7 @@ f5_gemm_args base_args(long long rows, int n_out, int k, int lda, int ldw, int b
   return a;
 }
 
-// Tile heuristic for the persistent GEMM (measured on B200, tools/gemm_sweep.py, profiles/):
-//  * enough work for >= 2 rounds of 256x256 CTA-pair tiles over the 74 SM pairs -> cta_group::2 256x256
-//    (1.30-1.35 PFLOP/s at M >= 15k: 3/4 of the shared-memory traffic per MMA cycle of the single-CTA kernel);
-//  * otherwise single-CTA 128x128 tiles, which balance better over 148 SMs when there are few tiles
-//    (M = 1876: all variants within 5 %, 128x128 never worse).
-// bn = 0: the GEMM planner picks the tile shape (gemm.cu: pick_tile)
-void set_tile(f5_gemm_args& a, long long, int, bool) {
-  a.bn = 0;
-  a.cta_pair = 0;
-}
+constexpr int kAutoTile = 0;  // bn = 0: the GEMM planner picks the tile shape per problem (gemm.cu: pick_tile)
 
 int build_step_plans(f5_engine* e, const Layout& L, const f5_sample_args* sa, StepPlans& P) {
   const f5_arch& A = e->arch;
@@ -314,8 +305,7 @@ int build_step_plans(f5_engine* e, const Layout& L, const f5_sample_args* sa, St
       RC(gemm_plan(&P.skip[i], L.cat, lw.w_skip, &a));
     }
     {
-      f5_gemm_args a = base_args(L.M1, 3 * inner, D, D, D, 128, F5_EPI_QKV_ROPE, F5_ACT_NONE);
-      set_tile(a, L.M1, 3 * inner, true);
+      f5_gemm_args a = base_args(L.M1, 3 * inner, D, D, D, kAutoTile, F5_EPI_QKV_ROPE, F5_ACT_NONE);
       a.bias = lw.b_qkv;
       a.out = L.qkv;
       a.ldo = 3 * inner;
@@ -327,8 +317,7 @@ int build_step_plans(f5_engine* e, const Layout& L, const f5_sample_args* sa, St
       RC(gemm_plan(&P.qkv[i], L.a, lw.w_qkv, &a));
     }
     {
-      f5_gemm_args a = base_args(L.M1, D, inner, inner, inner, 128, F5_EPI_RESID, F5_ACT_NONE);
-      set_tile(a, L.M1, D, true);
+      f5_gemm_args a = base_args(L.M1, D, inner, inner, inner, kAutoTile, F5_EPI_RESID, F5_ACT_NONE);
       a.bias = lw.b_out;
       a.resid = L.x;
       a.ldo = D;
@@ -342,16 +331,14 @@ int build_step_plans(f5_engine* e, const Layout& L, const f5_sample_args* sa, St
       RC(gemm_plan(&P.oproj[i], L.ao, lw.w_out, &a));
     }
     {
-      f5_gemm_args a = base_args(L.M1, F, D, D, D, 128, F5_EPI_F16, F5_ACT_GELU_TANH);
-      set_tile(a, L.M1, F, true);
+      f5_gemm_args a = base_args(L.M1, F, D, D, D, kAutoTile, F5_EPI_F16, F5_ACT_GELU_TANH);
       a.bias = lw.b_ff1;
       a.out = L.g;
       a.ldo = F;
       RC(gemm_plan(&P.ff1[i], L.a, lw.w_ff1, &a));
     }
     {
-      f5_gemm_args a = base_args(L.M1, D, F, F, F, 128, F5_EPI_RESID, F5_ACT_NONE);
-      set_tile(a, L.M1, D, true);
+      f5_gemm_args a = base_args(L.M1, D, F, F, F, kAutoTile, F5_EPI_RESID, F5_ACT_NONE);
       a.bias = lw.b_ff2;
       a.resid = L.x;
       a.ldo = D;
