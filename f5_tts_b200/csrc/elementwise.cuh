@@ -17,28 +17,35 @@ namespace f5 {
 
 template <int MODE>
 __global__ void __launch_bounds__(256) row_norm_kernel(const NormParams p) {
-  pdl_wait();
   pdl_launch_dependents();
-  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (row >= p.rows) return;
+  const int row = blockIdx.x * int(blockDim.x >> 5) + (threadIdx.x >> 5);  // one warp per row
   const int lane = lane_id();
   const int nv = p.D >> 7;  // float4 per lane (D multiple of 128, <= 1024)
-  const float4* xr = reinterpret_cast<const float4*>(p.x + (long long)row * p.D);
-  const long long so = p.step_ptr ? (long long)(*p.step_ptr) * p.step_stride : 0;
-  const float4* A = reinterpret_cast<const float4*>(p.a + so);
-  const float4* B = (MODE == 2) ? nullptr : reinterpret_cast<const float4*>(p.b + so);
   float4 v[8], ga[8], gb[8];
   float s = 0.f;
-  // issue every global load up front (row, scale, shift): one exposed L2 latency instead of two
+  // Scale / shift of this step: inside the engine they were written long before the producer of x (modulation table,
+  // step counter of the previous NFE step), so they are fetched BEFORE the programmatic-launch dependency wait — the
+  // block is already resident while the residual GEMM is still running, and only the x rows are left to read after it.
+  auto load_params = [&]() {
+    const long long so = p.step_ptr ? (long long)(*p.step_ptr) * p.step_stride : 0;
+    const float4* A = reinterpret_cast<const float4*>(p.a + so);
+    const float4* B = (MODE == 2) ? nullptr : reinterpret_cast<const float4*>(p.b + so);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (i < nv) {
+        ga[i] = __ldg(A + i * 32 + lane);
+        if (MODE != 2) gb[i] = __ldg(B + i * 32 + lane);
+      }
+  };
+  if (p.params_static && row < p.rows) load_params();
+  pdl_wait();
+  if (row >= p.rows) return;
+  const float4* xr = reinterpret_cast<const float4*>(p.x + (long long)row * p.D);
+  // issue every remaining global load up front: one exposed L2 latency
 #pragma unroll
   for (int i = 0; i < 8; ++i)
     if (i < nv) v[i] = xr[i * 32 + lane];
-#pragma unroll
-  for (int i = 0; i < 8; ++i)
-    if (i < nv) {
-      ga[i] = __ldg(A + i * 32 + lane);
-      if (MODE != 2) gb[i] = __ldg(B + i * 32 + lane);
-    }
+  if (!p.params_static) load_params();
 #pragma unroll
   for (int i = 0; i < 8; ++i)
     if (i < nv) s += v[i].x + v[i].y + v[i].z + v[i].w;

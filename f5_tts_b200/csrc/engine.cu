@@ -382,6 +382,7 @@ int norm_mod(const f5_engine* e, const Layout& L, const float* x, long long rows
   p.b = b;
   p.step_ptr = step_indexed ? L.step_ptr : nullptr;
   p.step_stride = step_indexed ? e->modW : 0;
+  p.params_static = 1;  // modulation table / gains: complete long before the GEMM that produces x
   if (diag_skip("norm")) return 0;
   return run_row_norm(mode, p, s);
 }

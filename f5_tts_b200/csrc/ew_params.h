@@ -14,6 +14,7 @@ struct NormParams {
   const float* b;  // MODE0: shift  MODE1: bias
   const int* step_ptr;
   long long step_stride;
+  int params_static;  // a / b / *step_ptr were not written by the kernel preceding this launch: fetch them before the PDL wait
 };
 
 struct DwConvLnParams {

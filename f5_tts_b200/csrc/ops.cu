@@ -3,6 +3,8 @@
 #include "fft.cuh"
 #include "internal.h"
 
+#include <cstdlib>
+
 namespace f5 {
 
 static inline int grid_for(long long n, int block, int cap = 148 * 16) {
@@ -17,7 +19,15 @@ int run_row_norm(int mode, const NormParams& p, cudaStream_t s) {
     set_error("row_norm: D must be a multiple of 128 and <= 1024 (got %d)", p.D);
     return -1;
   }
-  PdlLaunch L(dim3((p.rows + 7) / 8), dim3(256), 0, s);
+  // warps (= rows) per block: small blocks fit next to a still-running GEMM CTA (register file), so more of them are
+  // resident with their modulation rows prefetched when the producer finishes
+  static int wpb = 0;
+  if (wpb == 0) {
+    const char* e = getenv("F5_NORM_WARPS");
+    wpb = e ? atoi(e) : 4;  // cfg2 on B200: 55.17 / 54.91 / 54.83 ms per utterance with 8 / 4 / 2
+    if (wpb != 2 && wpb != 4 && wpb != 8) wpb = 4;
+  }
+  PdlLaunch L(dim3((p.rows + wpb - 1) / wpb), dim3(32 * wpb), 0, s);
   cudaError_t ce;
   if (mode == 0) ce = cudaLaunchKernelEx(&L.cfg, row_norm_kernel<0>, p);
   else if (mode == 1) ce = cudaLaunchKernelEx(&L.cfg, row_norm_kernel<1>, p);
