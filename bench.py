@@ -405,7 +405,7 @@ def main():
         roof["step_tensor"] = dict(flops_per_step=flops, achieved=round(step_tf, 1), peak=peaks["tf_sus"],
                                    unit="TFLOP/s", frac=round(step_tf / peaks["tf_sus"], 4),
                                    note="whole hot-path step (all kernels, launch gaps included) vs sustained bf16 peak")
-        cpu = None if args.no_cpu_baseline else cpu_leg(w)
+        cpu = None if (args.no_cpu_baseline or world > 1) else cpu_leg(w)  # timed at N = 1 only
         line = dict(metric="mel_frames_per_sec", value=value, unit="mel_frames/s", n_gpus=world, steps=args.steps,
                     warmup=args.warmup, ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None,
                     dtype="fp16 operands / fp32 accumulate+state", data="synthetic (random-init weights, released checkpoint layout)",
