@@ -1,0 +1,155 @@
+"""CPU: host logic of the inference-process layer — checkpoint loading in the released
+layouts, wav reading, and the chunk loop of infer_batch_process (slicing, RMS gain, cross-fade, spectrogram concat)
+with the sampler and vocoder replaced by recording fakes.  No kernel is called."""
+import os
+import wave
+
+import numpy as np
+import pytest
+import torch
+
+from f5_tts_b200 import infer
+from f5_tts_b200.model import CFM, DiT
+
+TINY = dict(dim=128, depth=2, heads=2, ff_mult=2, text_dim=64, conv_layers=1, text_mask_padding=False, pe_attn_head=1)
+
+
+def _vocab(tmp_path, n=40):
+    p = tmp_path / "vocab.txt"
+    p.write_text("\n".join([" "] + [chr(ord("a") + i % 26) + ("" if i < 26 else str(i)) for i in range(n - 1)]) + "\n")
+    return str(p), n
+
+
+def _reference_state(model):
+    g = torch.Generator().manual_seed(5)
+    return {k: torch.randn(v.shape, generator=g) * 0.05 for k, v in model.state_dict().items()}
+
+
+@pytest.mark.parametrize("fmt", ["safetensors", "pt_ema", "pt_model"])
+def test_load_model_and_checkpoint_layouts(tmp_path, fmt):
+    """utils_infer.py:190-232: EMA safetensors (`ema_model.` prefix + initted/step), .pt with ema_model_state_dict
+    (legacy mel_spec buffers dropped) and .pt with model_state_dict (use_ema=False)."""
+    vocab, n = _vocab(tmp_path)
+    probe = infer.load_model(DiT, TINY, "", vocab_file=vocab, device="cpu")
+    assert isinstance(probe, CFM) and probe.transformer.text_embed.text_embed.weight.shape[0] == n + 1
+    want = _reference_state(probe)
+    if fmt == "safetensors":
+        from safetensors.torch import save_file
+
+        sd = {"ema_model." + k: v for k, v in want.items()}
+        sd["initted"], sd["step"] = torch.tensor(True), torch.tensor(7)
+        path = str(tmp_path / "model.safetensors")
+        save_file(sd, path)
+        use_ema = True
+    elif fmt == "pt_ema":
+        sd = {"ema_model." + k: v for k, v in want.items()}
+        sd["initted"], sd["step"] = torch.tensor(True), torch.tensor(7)
+        sd["ema_model.mel_spec.mel_stft.mel_scale.fb"] = torch.zeros(3)        # legacy buffers (utils_infer.py:214-219)
+        sd["ema_model.mel_spec.mel_stft.spectrogram.window"] = torch.zeros(3)
+        path = str(tmp_path / "model.pt")
+        torch.save({"ema_model_state_dict": sd}, path)
+        use_ema = True
+    else:
+        path = str(tmp_path / "model.pt")
+        torch.save({"model_state_dict": want}, path)
+        use_ema = False
+    model = infer.load_model(DiT, TINY, path, vocab_file=vocab, use_ema=use_ema, device="cpu")
+    got = model.state_dict()
+    assert set(got) == set(want)
+    for k in want:
+        assert torch.equal(got[k].float(), want[k]), k
+    assert next(model.parameters()).dtype == torch.float32  # fp16 only on CUDA (utils_infer.py:190-199)
+
+
+def test_load_model_needs_vocab():
+    with pytest.raises(FileNotFoundError):
+        infer.load_model(DiT, TINY, "", vocab_file="", device="cpu")
+
+
+def test_load_wav_pcm16(tmp_path):
+    sr, n = 16000, 800
+    x = (np.sin(np.arange(n) * 0.05) * 12000).astype("<i2")
+    stereo = np.stack([x, -x], axis=1)
+    p = str(tmp_path / "a.wav")
+    with wave.open(p, "wb") as f:
+        f.setnchannels(2)
+        f.setsampwidth(2)
+        f.setframerate(sr)
+        f.writeframes(stereo.tobytes())
+    audio, got_sr = infer._load_wav(p)
+    assert got_sr == sr and audio.shape == (2, n) and audio.dtype == torch.float32
+    assert torch.allclose(audio[0], torch.from_numpy(x.astype(np.float32) / 32768.0))
+    assert torch.allclose(audio[1], -audio[0], atol=1 / 32768.0)
+
+
+class _FakeModel:
+    """Records the sampler calls of `_infer_basic` (utils_infer.py:477-520) and returns a ramp mel."""
+
+    def __init__(self):
+        self.calls = []
+
+    def sample(self, cond, text, duration, steps, cfg_strength, sway_sampling_coef):
+        self.calls.append(dict(cond=cond.clone(), text=text, duration=duration, steps=steps, cfg=cfg_strength,
+                               sway=sway_sampling_coef))
+        mel = torch.arange(duration, dtype=torch.float32).view(1, duration, 1).repeat(1, 1, 100)
+        return mel, None
+
+
+class _FakeVocoder:
+    def decode(self, mel):  # [1, 100, n] -> [1, 256 (n - 1)], constant 0.5 so gains are visible
+        return torch.full((1, 256 * (mel.shape[-1] - 1)), 0.5)
+
+
+def test_infer_batch_process_chunk_loop():
+    sr = infer.target_sample_rate
+    ref = torch.full((2, sr), 0.02)  # 1 s stereo, RMS 0.02 < target 0.1 -> gain 5 in, 1/5 out
+    ref_text = "hello there."
+    batches = ["first chunk of text.", "second one, a bit longer than the first."]
+    model, voc = _FakeModel(), _FakeVocoder()
+    out = list(infer.infer_batch_process((ref, sr), ref_text, batches, model, voc, nfe_step=7, cfg_strength=1.5,
+                                         sway_sampling_coef=-0.5, cross_fade_duration=0.1, device="cpu"))
+    assert len(out) == 1
+    wave_np, got_sr, spec = out[0]
+    assert got_sr == sr
+    ref_len = sr // infer.hop_length
+    assert len(model.calls) == 2
+    by_text = {}
+    for c in model.calls:
+        assert c["steps"] == 7 and c["cfg"] == 1.5 and c["sway"] == -0.5
+        assert c["cond"].shape == (1, sr)                                  # mono mix
+        assert torch.allclose(c["cond"], torch.full((1, sr), 0.1), atol=1e-6)  # RMS-normalised to 0.1
+        by_text[len(c["text"][0])] = c
+    # duration heuristic: ref frames + ref frames / ref bytes * gen bytes / speed (utils_infer.py:487-493)
+    rt = ref_text + " "
+    durs = [ref_len + int(ref_len / len(rt.encode()) * len(b.encode()) / 1.0) for b in batches]
+    assert sorted(c["duration"] for c in model.calls) == sorted(durs)
+    # per chunk: generated part only, vocoded, gain undone; then cross-faded
+    lens = [256 * (d - ref_len - 1) for d in durs]
+    fade = int(0.1 * sr)
+    assert len(wave_np) == lens[0] + lens[1] - fade
+    assert np.allclose(wave_np, 0.5 * 0.02 / 0.1, atol=1e-6)               # constant signal survives the linear fade
+    assert spec.shape == (100, (durs[0] - ref_len) + (durs[1] - ref_len))
+    assert spec[0, 0] == ref_len and spec[0, durs[0] - ref_len] == ref_len  # each chunk starts right after the prompt
+
+
+def test_infer_batch_process_streaming_and_short_text():
+    sr = infer.target_sample_rate
+    ref = torch.full((1, sr), 0.2)  # louder than target: no gain either way
+    model, voc = _FakeModel(), _FakeVocoder()
+    chunks = list(infer.infer_batch_process((ref, sr), "ok then.", ["hi."], model, voc, device="cpu", streaming=True,
+                                            chunk_size=1000))
+    ref_len = sr // infer.hop_length
+    # < 10 bytes of text -> local speed 0.3 (utils_infer.py:479-481)
+    dur = ref_len + int(ref_len / len("ok then. ".encode()) * len("hi.".encode()) / 0.3)
+    assert model.calls[0]["duration"] == dur
+    total = sum(len(c[0]) for c in chunks)
+    assert total == 256 * (dur - ref_len - 1) and all(c[1] == sr for c in chunks)
+    assert all(len(c[0]) <= 1000 for c in chunks)
+    assert np.allclose(np.concatenate([c[0] for c in chunks]), 0.5)
+
+
+def test_infer_process_empty_text(tmp_path):
+    sr = infer.target_sample_rate
+    ref = torch.full((1, 2 * sr), 0.1)
+    wav, got_sr, spec = infer.infer_process((ref, sr), "some reference text.", "", _FakeModel(), _FakeVocoder(), device="cpu")
+    assert wav is None and spec is None and got_sr == sr
