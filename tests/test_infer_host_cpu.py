@@ -113,12 +113,10 @@ def test_infer_batch_process_chunk_loop():
     assert got_sr == sr
     ref_len = sr // infer.hop_length
     assert len(model.calls) == 2
-    by_text = {}
     for c in model.calls:
         assert c["steps"] == 7 and c["cfg"] == 1.5 and c["sway"] == -0.5
         assert c["cond"].shape == (1, sr)                                  # mono mix
         assert torch.allclose(c["cond"], torch.full((1, sr), 0.1), atol=1e-6)  # RMS-normalised to 0.1
-        by_text[len(c["text"][0])] = c
     # duration heuristic: ref frames + ref frames / ref bytes * gen bytes / speed (utils_infer.py:487-493)
     rt = ref_text + " "
     durs = [ref_len + int(ref_len / len(rt.encode()) * len(b.encode()) / 1.0) for b in batches]
@@ -153,3 +151,39 @@ def test_infer_process_empty_text(tmp_path):
     ref = torch.full((1, 2 * sr), 0.1)
     wav, got_sr, spec = infer.infer_process((ref, sr), "some reference text.", "", _FakeModel(), _FakeVocoder(), device="cpu")
     assert wav is None and spec is None and got_sr == sr
+
+
+def test_api_model_table_matches_reference_configs():
+    """api.MODEL_ARCH restates configs/*.yaml `model.arch` (hydra is not installed here); pinned against the reference's
+    own files when the reference tree is present (it is not on the GPU box)."""
+    import yaml
+
+    from f5_tts_b200 import api
+    from f5_tts_b200.model import UNetT
+
+    cfg_dir = "/root/reference/src/f5_tts/configs"
+    if not os.path.isdir(cfg_dir):
+        pytest.skip("reference tree not present (GPU box)")
+    for name, (cls, arch) in api.MODEL_ARCH.items():
+        ref = yaml.safe_load(open(os.path.join(cfg_dir, name + ".yaml")))["model"]
+        assert ref["backbone"] == cls.__name__ and (cls is UNetT) == (ref["backbone"] == "UNetT")
+        ref_arch = {k: v for k, v in ref["arch"].items() if k != "checkpoint_activations"}  # training-only switch
+        assert {k: arch[k] for k in ref_arch if k in arch} == {k: v for k, v in ref_arch.items() if k in arch}, name
+        assert set(arch) <= set(ref_arch), (name, set(arch) - set(ref_arch))
+        for k in set(ref_arch) - set(arch):  # anything we leave out must be the reference's inactive default
+            assert ref_arch[k] in (None, False, "torch"), (name, k, ref_arch[k])
+        assert ref["mel_spec"]["mel_spec_type"] == "vocos" and ref["mel_spec"]["n_mel_channels"] == infer.n_mel_channels
+        assert ref["mel_spec"]["hop_length"] == infer.hop_length and ref["mel_spec"]["n_fft"] == infer.n_fft
+
+
+def test_api_rejects_unknown_model_and_exports_wav(tmp_path):
+    from f5_tts_b200 import api
+
+    with pytest.raises(ValueError):
+        api.F5TTS(model="nope", ckpt_file="x", vocab_file="y")
+    obj = api.F5TTS.__new__(api.F5TTS)  # export helpers do not need a loaded model
+    obj.target_sample_rate = 24000
+    p = str(tmp_path / "o.wav")
+    obj.export_wav(np.array([0.0, 0.5, -2.0], dtype=np.float32), p)
+    audio, sr = infer._load_wav(p)
+    assert sr == 24000 and torch.allclose(audio[0], torch.tensor([0.0, 0.5, -1.0]), atol=1e-4)
