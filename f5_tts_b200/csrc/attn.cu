@@ -1,5 +1,6 @@
 // Host side of the tcgen05 attention kernel + C entry point f5_attention.
 #include "attn.cuh"
+#include "attn_splitkv.cuh"
 #include "internal.h"
 
 #include <cstdlib>
@@ -30,6 +31,17 @@ int attn_plan(AttnPlan* pl, const void* qkv, void* out, int batches, int seq, in
       ts = e ? atoi(e) : 1;  // measured: 22.6 us (on) vs 24.4 us (off) at Be=2, seq=938
     }
     pl->p.turnstile = ts;
+    static int var = -1;
+    if (var < 0) {
+      const char* e = getenv("F5_ATTN_VARIANT");
+      var = (e && atoi(e) == 6) ? 6 : 3;  // 6: experimental split-KV kernel, not validated on hardware yet
+    }
+    pl->p.variant = var;
+    if (var == 6) {
+      rc = encode_tmap_f16(&pl->tm_kv64, qkv, (uint64_t)3 * inner, (uint64_t)seq, (uint64_t)batches, (uint64_t)3 * inner * 2,
+                           (uint64_t)seq * 3 * inner * 2, 64, 64, 3);
+      if (rc) return rc;
+    }
   }
   {
     static long long* trace = nullptr;
@@ -51,13 +63,24 @@ int attn_configure() {
                           "cudaFuncSetAttribute(attn smem)"))
     return rc;
   cudaFuncSetAttribute(attn_fwd_tcgen05_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  if (int rc = check_cuda(cudaFuncSetAttribute(attn_fwd_splitkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               (int)kSkvSmem),
+                          "cudaFuncSetAttribute(split-KV attn smem)"))
+    return rc;
+  cudaFuncSetAttribute(attn_fwd_splitkv_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   return 0;
 }
 
 int attn_run(const AttnPlan& pl, cudaStream_t s) {
   if (int rc = configure_kernels()) return rc;
-  PdlLaunch L(pl.grid, dim3(kAttnThreads), kAttnSmem, s);
-  if (int rc = check_cuda(cudaLaunchKernelEx(&L.cfg, attn_fwd_tcgen05_kernel, pl.tm, pl.p), "attention launch")) return rc;
+  if (pl.p.variant == 6) {
+    PdlLaunch L(pl.grid, dim3(kSkvThreads), kSkvSmem, s);
+    if (int rc = check_cuda(cudaLaunchKernelEx(&L.cfg, attn_fwd_splitkv_kernel, pl.tm, pl.tm_kv64, pl.p), "split-KV attention launch"))
+      return rc;
+  } else {
+    PdlLaunch L(pl.grid, dim3(kAttnThreads), kAttnSmem, s);
+    if (int rc = check_cuda(cudaLaunchKernelEx(&L.cfg, attn_fwd_tcgen05_kernel, pl.tm, pl.p), "attention launch")) return rc;
+  }
   count_launch();
   return check_launch("attn_fwd_tcgen05_kernel launch");
 }

@@ -57,6 +57,7 @@ int gemm_run(const GemmPlan& plan, cudaStream_t s);
 
 struct AttnPlan {
   CUtensorMap tm;
+  CUtensorMap tm_kv64;  // 64-row K / V boxes (experimental split-KV kernel only)
   AttnParams p;
   dim3 grid;
 };

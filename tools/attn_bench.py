@@ -1,4 +1,8 @@
-"""GPU tool: time the attention kernel at the workload shapes."""
+"""GPU tool: time the attention kernel at the workload shapes.
+
+A/B the experimental split-KV kernel with  F5_ATTN_VARIANT=6 python tools/attn_bench.py  (default: production kernel);
+parity first:  F5_ATTN_VARIANT=6 python -m pytest tests/test_gpu_kernels.py -q -m gpu -k attention
+"""
 import sys
 
 import torch
