@@ -63,17 +63,21 @@ int attn_configure() {
                           "cudaFuncSetAttribute(attn smem)"))
     return rc;
   cudaFuncSetAttribute(attn_fwd_tcgen05_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-  if (int rc = check_cuda(cudaFuncSetAttribute(attn_fwd_splitkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               (int)kSkvSmem),
-                          "cudaFuncSetAttribute(split-KV attn smem)"))
-    return rc;
-  cudaFuncSetAttribute(attn_fwd_splitkv_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   return 0;
 }
 
 int attn_run(const AttnPlan& pl, cudaStream_t s) {
   if (int rc = configure_kernels()) return rc;
   if (pl.p.variant == 6) {
+    static int configured = 0;  // the experimental kernel is configured only when it is asked for
+    if (!configured) {
+      if (int rc = check_cuda(cudaFuncSetAttribute(attn_fwd_splitkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   (int)kSkvSmem),
+                              "cudaFuncSetAttribute(split-KV attn smem)"))
+        return rc;
+      cudaFuncSetAttribute(attn_fwd_splitkv_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+      configured = 1;
+    }
     PdlLaunch L(pl.grid, dim3(kSkvThreads), kSkvSmem, s);
     if (int rc = check_cuda(cudaLaunchKernelEx(&L.cfg, attn_fwd_splitkv_kernel, pl.tm, pl.tm_kv64, pl.p), "split-KV attention launch"))
       return rc;
