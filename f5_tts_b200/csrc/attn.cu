@@ -34,7 +34,7 @@ int attn_plan(AttnPlan* pl, const void* qkv, void* out, int batches, int seq, in
     static int var = -1;
     if (var < 0) {
       const char* e = getenv("F5_ATTN_VARIANT");
-      var = (e && atoi(e) == 6) ? 6 : 3;  // 6: experimental split-KV kernel, not validated on hardware yet
+      var = (e && atoi(e) == 6) ? 6 : 3;  // 6: experimental split-KV kernel (parity-green on B200, not timed yet)
     }
     pl->p.variant = var;
     if (var == 6) {

@@ -1,6 +1,7 @@
-// EXPERIMENTAL (selected only by F5_ATTN_VARIANT=6, never by default; written at the end of round 1 and not yet run on
-// hardware — validate with `F5_ATTN_VARIANT=6 pytest tests/test_gpu_kernels.py -k attention` and tools/attn_bench.py
-// before making it the default).
+// EXPERIMENTAL (selected only by F5_ATTN_VARIANT=6, never by default).  Written at the end of round 1: it passes the
+// attention parity tests on B200 (`F5_ATTN_VARIANT=6 pytest tests/test_gpu_kernels.py -m gpu -k attention`: 7 / 7), but the
+// round's GPU budget ran out before it could be TIMED — run tools/attn_bench.py with and without F5_ATTN_VARIANT=6 and the
+// end-to-end tests before making it the default.
 //
 // Split-KV variant of the dim_head-64 flash-attention forward (same contract as attn_fwd_tcgen05_kernel, attn.cuh).
 // Why: at cfg2 an SM owns only ~1.6 query tiles, i.e. two softmax warps per scheduler.  Measurements (profiles/README.md,

@@ -53,7 +53,7 @@ struct AttnParams {
   __half* out;        // [Be*seq, inner]
   long long* dbg_ts;  // optional [CTAs][16] phase-cycle trace (diagnostics; NULL in production)
   int turnstile;      // 1: serialise the exp2 loops of the two softmax warpgroups (ping-pong); 0: free-running
-  int variant;        // 3 = production kernel (attn.cuh); 6 = EXPERIMENTAL split-KV kernel (attn_splitkv.cuh, F5_ATTN_VARIANT=6)
+  int variant;        // 3 = production kernel (attn.cuh); 6 = EXPERIMENTAL split-KV kernel (attn_splitkv.cuh, F5_ATTN_VARIANT=6; parity-green, untimed)
 };
 
 constexpr int kAttnThreads = 320;   // TMA warp + MMA warp + 2 softmax warpgroups
