@@ -238,46 +238,57 @@ def host_cores():
     return n, n
 
 
-def cpu_leg(w, nfe_pair=(1, 3)):
-    """CPU oracle (port of the reference) on all host cores; NFE a and b timed, scaled linearly to the workload NFE."""
-    from oracle import f5_oracle as O
+class CpuOracle:
+    """CPU oracle (port of the reference, fp32) on all host cores.  Built once (1.3 GB of synthetic weights, one
+    untimed warm-up); `measure(budget_s)` times NFE 1 and NFE b, with b chosen so that the sample costs about `budget_s`
+    seconds of CPU work, and scales linearly to the workload NFE."""
 
-    cores, threads = host_cores()
-    torch.set_num_threads(threads)
-    cfg = getattr(O, w["arch"])()
-    sd = O.synthetic_state_dict(cfg, seed=1234)
-    vsd = O.synthetic_vocos_state_dict()
-    wav, text, duration, lens = synth_inputs(w)
-    B = w["B"]
+    def __init__(self, w):
+        from oracle import f5_oracle as O
 
-    def run(n):
+        self.O, self.w = O, w
+        self.cores, self.threads = host_cores()
+        torch.set_num_threads(self.threads)
+        self.cfg = getattr(O, w["arch"])()
+        self.sd = O.synthetic_state_dict(self.cfg, seed=1234)
+        self.vsd = O.synthetic_vocos_state_dict()
+        self.wav, self.text, self.duration, self.lens = synth_inputs(w)
+        self.run(1)  # untimed warm-up: thread pool, oneDNN primitive caches, first touch of the weights
+
+    def run(self, n):
+        O, w = self.O, self.w
         t0 = time.perf_counter()
-        if B == 1:
-            res = O.sample(sd, cfg, wav, text, int(duration[0]), steps=n, cfg_strength=CFG_STRENGTH,
-                           sway_sampling_coef=SWAY, seed=0)
-            ref = wav.shape[-1] // 256
+        if w["B"] == 1:
+            res = O.sample(self.sd, self.cfg, self.wav, self.text, int(self.duration[0]), steps=n,
+                           cfg_strength=CFG_STRENGTH, sway_sampling_coef=SWAY, seed=0)
+            ref = self.wav.shape[-1] // 256
         else:
-            cond = O.mel_spectrogram(wav).permute(0, 2, 1)
-            res = O.sample(sd, cfg, cond, text, duration, lens=lens, steps=n, cfg_strength=CFG_STRENGTH,
-                           sway_sampling_coef=SWAY, seed=0)
-            ref = int(lens.min())
+            cond = O.mel_spectrogram(self.wav).permute(0, 2, 1)
+            res = O.sample(self.sd, self.cfg, cond, self.text, self.duration, lens=self.lens, steps=n,
+                           cfg_strength=CFG_STRENGTH, sway_sampling_coef=SWAY, seed=0)
+            ref = int(self.lens.min())
         t1 = time.perf_counter()
-        O.vocos_decode(vsd, res.out[:, ref:, :].permute(0, 2, 1))
+        O.vocos_decode(self.vsd, res.out[:, ref:, :].permute(0, 2, 1))
         t2 = time.perf_counter()
         return t1 - t0, t2 - t1
 
-    a, b = nfe_pair
-    run(1)  # untimed warm-up: thread pool, oneDNN primitive caches, first-touch of 1.3 GB of weights
-    ta, tv = run(a)
-    tb, _ = run(b)
-    per = (tb - ta) / (b - a)
-    fixed = max(ta - a * per, 0.0)
-    total = fixed + w["nfe"] * per + tv
-    gen = sum(f - r for f, r in zip(w["frames"], w["ref"]))
-    return dict(value=gen / total, unit="mel_frames/s", cores=cores, threads=threads, kind="port",
-                sample=f"oracle fp32 CPU: NFE {a} and {b} of {w['nfe']} timed ({ta + tb + tv:.1f} s), scaled linearly "
-                       f"(per-NFE {per:.2f} s, fixed {fixed:.2f} s, vocoder {tv:.3f} s)",
-                rtf=total / (gen * 256 / 24000.0), seconds_full_extrapolated=total)
+    def measure(self, budget_s=12.0):
+        w = self.w
+        ta, tv = self.run(1)
+        b = max(3, min(w["nfe"], 1 + int(budget_s / max(ta, 1e-3))))
+        tb, _ = self.run(b)
+        per = (tb - ta) / (b - 1)
+        fixed = max(ta - per, 0.0)
+        total = fixed + w["nfe"] * per + tv
+        gen = sum(f - r for f, r in zip(w["frames"], w["ref"]))
+        return dict(value=gen / total, unit="mel_frames/s", cores=self.cores, threads=self.threads, kind="port",
+                    sample=f"oracle fp32 CPU: NFE 1 and {b} of {w['nfe']} timed ({ta + tb + tv:.1f} s), scaled linearly "
+                           f"(per-NFE {per:.2f} s, fixed {fixed:.2f} s, vocoder {tv:.3f} s)",
+                    rtf=total / (gen * 256 / 24000.0), seconds_full_extrapolated=total)
+
+
+def cpu_leg(w, budget_s=12.0):
+    return CpuOracle(w).measure(budget_s)
 
 
 def main():
@@ -303,8 +314,11 @@ def main():
         if rank != 0:
             return
         vals, last = [], None
-        for i in range(args.warmup + args.steps):
-            last = cpu_leg(w, nfe_pair=(1, 3))
+        oracle = CpuOracle(w)
+        n_runs = args.warmup + args.steps
+        budget = min(15.0, max(2.0, 150.0 / n_runs))  # the whole reference run stays within a few minutes
+        for i in range(n_runs):
+            last = oracle.measure(budget)
             if i >= args.warmup:
                 vals.append(last["value"])
         v = statistics.mean(vals)
