@@ -187,3 +187,37 @@ def test_api_rejects_unknown_model_and_exports_wav(tmp_path):
     obj.export_wav(np.array([0.0, 0.5, -2.0], dtype=np.float32), p)
     audio, sr = infer._load_wav(p)
     assert sr == 24000 and torch.allclose(audio[0], torch.tensor([0.0, 0.5, -1.0]), atol=1e-4)
+
+
+def test_load_vocoder_local_layout(tmp_path):
+    """utils_infer.py:118-129: `config.yaml` + `pytorch_model.bin` of charactr/vocos-mel-24khz read from a local folder;
+    the state dict (incl. the feature-extractor buffers the checkpoint carries) loads with strict=True."""
+    import yaml
+
+    from oracle import f5_oracle as O  # test-only: synthetic weights in the released vocos key layout
+
+    cfg = {
+        "feature_extractor": {"class_path": "vocos.feature_extractors.MelSpectrogramFeatures",
+                              "init_args": {"sample_rate": 24000, "n_fft": 1024, "hop_length": 256, "n_mels": 100,
+                                            "padding": "center"}},
+        "backbone": {"class_path": "vocos.models.VocosBackbone",
+                     "init_args": {"input_channels": 100, "dim": 512, "intermediate_dim": 1536, "num_layers": 8}},
+        "head": {"class_path": "vocos.heads.ISTFTHead",
+                 "init_args": {"dim": 512, "n_fft": 1024, "hop_length": 256, "padding": "center"}},
+    }
+    (tmp_path / "config.yaml").write_text(yaml.safe_dump(cfg))
+    sd = O.synthetic_vocos_state_dict()
+    # the released checkpoint also carries the (unused at decode time) feature-extractor buffers
+    sd["feature_extractor.mel_spec.spectrogram.window"] = torch.hann_window(1024)
+    sd["feature_extractor.mel_spec.mel_scale.fb"] = O.mel_filterbank()
+    torch.save(sd, str(tmp_path / "pytorch_model.bin"))
+    voc = infer.load_vocoder("vocos", is_local=True, local_path=str(tmp_path), device="cpu")
+    got = voc.state_dict()
+    assert set(got) == set(sd)
+    for k, v in sd.items():
+        assert torch.equal(got[k], v), k
+    assert not voc.training
+    with pytest.raises(NotImplementedError):
+        infer.load_vocoder("bigvgan", is_local=True, local_path=str(tmp_path), device="cpu")
+    with pytest.raises(Exception):  # decode has no CPU path
+        voc.decode(torch.zeros(1, 100, 8))
