@@ -149,6 +149,7 @@ __global__ void text_gather_kernel(const TextGatherParams p) {
   const bool valid = p.valid_len == nullptr || n < p.valid_len[b];
   long long id = 0;
   if (n < p.nt && valid) id = p.ids[(long long)b * p.nt + n] + 1;
+  id = id < 0 ? 0 : (id >= p.num_embeds ? p.num_embeds - 1 : id);  // never read outside the table
   if (variant == 0 && threadIdx.x == 0) p.filler[r] = (id == 0) ? 1 : 0;
   if (variant == 1) id = 0;
   const int half = p.Td / 2;
@@ -259,6 +260,7 @@ __global__ void cfg_euler_kernel(const EulerParams p) {
   pdl_launch_dependents();
   const int k = *p.step_ptr;
   const float dt = p.dt[k];
+  const SampleIo io = *p.io;
   const long long total = (long long)p.BN * p.mel;
   const long long null_off = (long long)p.B * p.seq_tok * p.mel;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -271,11 +273,11 @@ __global__ void cfg_euler_kernel(const EulerParams p) {
     float g = pr;
     if (p.packed) {
       const float nu = p.v[null_off + vi];
-      g = pr + (pr - nu) * p.cfg;
+      g = pr + (pr - nu) * io.cfg;
     }
-    const float yn = p.y[i] + dt * g;
-    p.y[i] = yn;
-    if (p.traj) p.traj[(long long)(k + 1) * total + i] = yn;
+    const float yn = io.y[i] + dt * g;
+    io.y[i] = yn;
+    if (io.traj) io.traj[(long long)(k + 1) * total + i] = yn;
     const __half h = __float2half_rn(yn);
     p.xin[r * p.Kpad + c] = h;
     if (p.packed) p.xin[(r + p.BN) * p.Kpad + c] = h;

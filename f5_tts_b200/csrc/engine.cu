@@ -13,6 +13,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <vector>
 
@@ -40,6 +41,7 @@ struct Layout {
   long long M, M1;
   // common
   int* step_ptr;
+  SampleIo* io;     // caller tensors + cfg scale of THIS call, read by the step kernels through the workspace
   float* dt;
   float* t_dev;
   float *rope_cos, *rope_sin;
@@ -70,11 +72,28 @@ struct Layout {
 
 using namespace f5;
 
-struct GraphEntry {
+// One instantiated step graph.  The graph touches only the workspace: the caller's tensors (y, trajectory) and the CFG
+// scale reach the kernels through the SampleIo block the prologue writes into the workspace, so the cache key is the
+// workspace address plus the shape parameters the layout / kernel plans depend on — a fresh `y` or `trajectory`
+// allocation per call no longer forces a re-capture.  Entries are reference-counted: a launch in flight on one thread
+// keeps its graph alive while another thread evicts it.
+struct GraphHolder {
+  cudaGraphExec_t exec = nullptr;
+  int nodes = 0;  // kernel/memcpy nodes per replay (for the launch counter)
+  ~GraphHolder() {
+    if (exec) cudaGraphExecDestroy(exec);
+  }
+};
+struct GraphKey {
   const void* ws;
-  f5_sample_args key;
-  cudaGraphExec_t exec;
-  int nodes;  // kernel/memcpy nodes per replay (for the launch counter)
+  int B, N, steps, packed, masked;
+  bool operator==(const GraphKey& o) const {
+    return ws == o.ws && B == o.B && N == o.N && steps == o.steps && packed == o.packed && masked == o.masked;
+  }
+};
+struct GraphEntry {
+  GraphKey key;
+  std::shared_ptr<GraphHolder> g;
 };
 
 struct f5_engine {
@@ -99,6 +118,7 @@ static void plan_layout(const f5_engine* e, Layout& L, void* ws, int B, int N, i
   L.M1 = (long long)L.Be * L.seq;
   const int D = A.dim, Td = A.text_dim, F = A.ff_inner;
   L.step_ptr = bp.take<int>(64);
+  L.io = bp.take<SampleIo>(1);
   L.dt = bp.take<float>(steps + 1);
   L.t_dev = bp.take<float>(steps + 1);
   L.rope_cos = bp.take<float>((size_t)L.seq * 32);
@@ -182,8 +202,7 @@ int f5_engine_create(const f5_arch* arch, const f5_weights* weights, f5_engine**
 
 void f5_engine_destroy(f5_engine* e) {
   if (!e) return;
-  for (auto& g : e->graphs) cudaGraphExecDestroy(g.exec);
-  delete e;
+  delete e;  // graph holders destroy their executables
 }
 
 size_t f5_sample_workspace_bytes(const f5_engine* e, int B, int N, int steps, float cfg_strength) {
@@ -363,12 +382,16 @@ int build_step_plans(f5_engine* e, const Layout& L, const f5_sample_args* sa, St
   return 0;
 }
 
-// F5_DIAG_SKIP="norm,attn,qkv,out,ff1,ff2,conv" removes kernels from the step schedule (timing decomposition only:
-// results are wrong).  Never set in production.
+// Instrumented build (make TRACE=1) only: F5_DIAG_SKIP="norm,attn,qkv,out,ff1,ff2,conv" removes kernels from the step
+// schedule (timing decomposition; results are wrong).  The production library has no such switch.
+#ifdef F5_TRACE
 static bool diag_skip(const char* what) {
   static const char* v = getenv("F5_DIAG_SKIP");
   return v != nullptr && strstr(v, what) != nullptr;
 }
+#else
+static constexpr bool diag_skip(const char*) { return false; }
+#endif
 
 int norm_mod(const f5_engine* e, const Layout& L, const float* x, long long rows, int mode, const float* a,
              const float* b, bool step_indexed, cudaStream_t s) {
@@ -433,9 +456,8 @@ int run_step(f5_engine* e, const Layout& L, const f5_sample_args* sa, const Step
   }
   RC(gemm_run(P.out_proj, s));
   EulerParams ep{};
-  ep.y = sa->y;
+  ep.io = L.io;
   ep.v = L.v;
-  ep.traj = sa->trajectory;
   ep.xin = L.xin;
   ep.dt = L.dt;
   ep.step_ptr = L.step_ptr;
@@ -447,7 +469,6 @@ int run_step(f5_engine* e, const Layout& L, const f5_sample_args* sa, const Step
   ep.seq_tok = L.seq;
   ep.tok_off = dit ? 0 : 1;
   ep.B = L.B;
-  ep.cfg = sa->cfg_strength;
   return run_cfg_euler(ep, s);
 }
 
@@ -463,6 +484,8 @@ int run_prologue(f5_engine* e, const Layout& L, const f5_sample_args* sa, cudaSt
   RC(check_cuda(cudaMemcpyAsync(L.dt, dt.data(), sizeof(float) * (S + 1), cudaMemcpyHostToDevice, s), "dt h2d"));
   RC(check_cuda(cudaMemcpyAsync(L.t_dev, sa->t, sizeof(float) * (S + 1), cudaMemcpyHostToDevice, s), "t h2d"));
   RC(check_cuda(cudaMemsetAsync(L.step_ptr, 0, sizeof(int) * 64, s), "step memset"));
+  SampleIo io{sa->y, sa->trajectory, sa->cfg_strength};
+  RC(check_cuda(cudaMemcpyAsync(L.io, &io, sizeof(io), cudaMemcpyHostToDevice, s), "io h2d"));
   if (masked) {
     // row_len[Be] = duration (+1 for the UNetT time token, unett.py:274-275); kv_len likewise
     std::vector<int> hd(B);
@@ -499,6 +522,7 @@ int run_prologue(f5_engine* e, const Layout& L, const f5_sample_args* sa, cudaSt
   tp.Td = Td;
   tp.valid_len = (dit && masked) ? L.valid_len : nullptr;
   tp.table = W.text_table;
+  tp.num_embeds = A.text_num_embeds + 1;
   tp.add_pos = A.conv_layers > 0;
   tp.out = L.tx;
   tp.filler = L.filler;
@@ -560,12 +584,6 @@ int copy_v_out(const f5_engine* e, const Layout& L, const f5_sample_args* sa, cu
   return 0;
 }
 
-bool same_key(const f5_sample_args& a, const f5_sample_args& b) {
-  return a.B == b.B && a.N == b.N && a.nt == b.nt && a.steps == b.steps && a.text == b.text &&
-         a.step_cond == b.step_cond && a.y == b.y && a.duration == b.duration && a.trajectory == b.trajectory &&
-         (a.cfg_strength < 1e-5f) == (b.cfg_strength < 1e-5f) && a.cfg_strength == b.cfg_strength;
-}
-
 }  // namespace
 
 extern "C" int f5_sample(f5_engine* e, const f5_sample_args* sa, void* workspace, size_t ws_bytes, f5_stream_t stream) {
@@ -585,21 +603,19 @@ extern "C" int f5_sample(f5_engine* e, const f5_sample_args* sa, void* workspace
     return -1;
   }
   RC(run_prologue(e, L, sa, s));
-  cudaGraphExec_t exec = nullptr;
-  int nodes = 0;
   if (sa->use_graph) {
-    std::lock_guard<std::mutex> lk(e->mu);
-    for (auto& g : e->graphs)
-      if (g.ws == workspace && same_key(g.key, *sa)) {
-        exec = g.exec;
-        nodes = g.nodes;
-      }
-    if (!exec) {
+    const GraphKey key{workspace, sa->B, sa->N, sa->steps, L.packed, sa->duration != nullptr ? 1 : 0};
+    std::shared_ptr<GraphHolder> g;
+    {
+      std::lock_guard<std::mutex> lk(e->mu);
+      for (auto& en : e->graphs)
+        if (en.key == key) g = en.g;
+    }
+    if (!g) {
+      // Capture outside the engine mutex (thread-local capture mode: concurrent sample() calls capture independently)
+      // on a private stream — the caller's stream may be the legacy default stream, which cannot capture.
       StepPlans P;
       RC(build_step_plans(e, L, sa, P));
-      cudaGraph_t graph;
-      // capture on a private stream (the caller's stream may be the legacy default stream, which cannot capture);
-      // the instantiated graph is then launched into the caller's stream.
       cudaStream_t cs;
       RC(check_cuda(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking), "capture stream"));
       if (int brc = check_cuda(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal), "begin capture")) {
@@ -607,27 +623,31 @@ extern "C" int f5_sample(f5_engine* e, const f5_sample_args* sa, void* workspace
         return brc;
       }
       const unsigned long long before = f5_launch_count();
-      int rc = run_step(e, L, sa, P, cs);
-      cudaError_t ce = cudaStreamEndCapture(cs, &graph);
+      const int rc = run_step(e, L, sa, P, cs);
+      cudaGraph_t graph = nullptr;
+      const cudaError_t ce = cudaStreamEndCapture(cs, &graph);
       cudaStreamDestroy(cs);
       count_launch(-(int)(f5_launch_count() - before));  // captured, not launched
-      if (rc) return rc;
-      RC(check_cuda(ce, "end capture"));
+      if (rc || ce != cudaSuccess) {
+        if (graph) cudaGraphDestroy(graph);
+        return rc ? rc : check_cuda(ce, "end capture");
+      }
+      g = std::make_shared<GraphHolder>();
       size_t nn = 0;
       cudaGraphGetNodes(graph, nullptr, &nn);
-      nodes = (int)nn;
-      RC(check_cuda(cudaGraphInstantiate(&exec, graph, 0), "graph instantiate"));
+      g->nodes = (int)nn;
+      const cudaError_t ie = cudaGraphInstantiate(&g->exec, graph, 0);
       cudaGraphDestroy(graph);
-      if (e->graphs.size() >= 8) {
-        cudaGraphExecDestroy(e->graphs.front().exec);
-        e->graphs.erase(e->graphs.begin());
+      if (ie != cudaSuccess) {
+        g->exec = nullptr;
+        return check_cuda(ie, "graph instantiate");
       }
-      e->graphs.push_back(GraphEntry{workspace, *sa, exec, nodes});
+      std::lock_guard<std::mutex> lk(e->mu);
+      if (e->graphs.size() >= 16) e->graphs.erase(e->graphs.begin());  // holder is freed when its last user is done
+      e->graphs.push_back(GraphEntry{key, g});
     }
-    for (int k = 0; k < sa->steps; ++k) {
-      RC(check_cuda(cudaGraphLaunch(exec, s), "graph launch"));
-    }
-    count_launch(nodes * sa->steps);
+    for (int k = 0; k < sa->steps; ++k) RC(check_cuda(cudaGraphLaunch(g->exec, s), "graph launch"));
+    count_launch(g->nodes * sa->steps);
     return copy_v_out(e, L, sa, s);
   }
   StepPlans P;

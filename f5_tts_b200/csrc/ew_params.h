@@ -33,6 +33,8 @@ struct TextGatherParams {
   int B, nt, N, Td;
   const int* valid_len;  // [B] per-sample valid positions or null
   const float* table;    // [V+1, Td]
+  int num_embeds;        // V + 1 rows; ids outside [0, V] are clamped (the reference's nn.Embedding raises; the host
+                         // side validates ids before the call)
   int add_pos;           // conv_layers > 0
   float* out;            // [2B, N, Td]
   uint8_t* filler;       // [B, N]
@@ -46,10 +48,17 @@ struct PackParams {
   const float* text;       // [2B, N, Td] fp32 (cond variant first)
 };
 
+// Caller-owned tensors and scalars of one sample() call.  The step kernels read them from this block inside the
+// workspace (written by the prologue), so a captured step graph does not bake the caller's pointers in.
+struct SampleIo {
+  float* y;     // [B*N, mel] ODE state
+  float* traj;  // [steps+1, B*N, mel] or null
+  float cfg;    // classifier-free-guidance scale
+};
+
 struct EulerParams {
-  float* y;        // [B*N, mel]
+  const SampleIo* io;
   const float* v;  // [Be*N, mel]
-  float* traj;     // [steps+1, B*N, mel] or null
   __half* xin;
   const float* dt;  // [steps] device
   int* step_ptr;
@@ -58,7 +67,6 @@ struct EulerParams {
   int seq_tok;   // rows per sample in v (N for DiT, N + 1 for UNetT)
   int tok_off;   // first frame row inside a sample of v (0 DiT, 1 UNetT: skips the time token, unett.py:305)
   int B;
-  float cfg;
 };
 
 }  // namespace f5

@@ -4,6 +4,7 @@
 #include <cstring>
 #include <cstdlib>
 #include <atomic>
+#include <mutex>
 
 #include "gemm.cuh"
 #include "internal.h"
@@ -110,9 +111,27 @@ static int configure_inst() {
   if (pl.pair && pl.bn == BN_ && pl.epi == EPI_ && pl.act == ACT_ && !pl.conv)    \
     return launch_inst<BN_, ST_, EPI_, ACT_, false, true>(pl, s);
 
+// cudaFuncSetAttribute is per device: the configured flag and the SM count are tracked per device ordinal, so one
+// process may drive engines on several GPUs.
+namespace {
+constexpr int kMaxDevices = 64;
+struct DeviceState {
+  bool configured = false;
+  int sms = 0;
+};
+DeviceState g_dev[kMaxDevices];
+std::mutex g_dev_mu;
+int current_device() {
+  int d = 0;
+  cudaGetDevice(&d);
+  return (d >= 0 && d < kMaxDevices) ? d : 0;
+}
+}  // namespace
+
 int configure_kernels() {
-  static std::atomic<int> done{0};
-  if (done.load()) return 0;
+  const int dev = current_device();
+  std::lock_guard<std::mutex> lk(g_dev_mu);
+  if (g_dev[dev].configured) return 0;
   if (int rc = configure_inst<64, 7, EPI_F16, ACT_NONE, false>()) return rc;
   if (int rc = configure_inst<64, 7, EPI_F16, ACT_GELU_TANH, false>()) return rc;
   if (int rc = configure_inst<64, 7, EPI_F16, ACT_GELU_ERF, false>()) return rc;
@@ -145,25 +164,29 @@ int configure_kernels() {
   if (int rc = configure_inst<128, 6, EPI_RESID, ACT_NONE, false, true>()) return rc;
   if (int rc = configure_inst<128, 6, EPI_QKV_ROPE, ACT_NONE, false, true>()) return rc;
   if (int rc = attn_configure()) return rc;
-  done.store(1);
+  g_dev[dev].configured = true;
   return 0;
 }
 
 bool pdl_enabled() {
+#ifdef F5_TRACE  // diagnostic build only: F5_PDL=0 launches without programmatic dependent launch
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("F5_PDL");
     v = (e && e[0] == '0') ? 0 : 1;
   }
   return v != 0;
+#else
+  return true;
+#endif
 }
 
 int num_sms() {
-  static int n = 0;
+  const int dev = current_device();
+  int n = g_dev[dev].sms;  // written once per device; a racing first call computes the same value
   if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    g_dev[dev].sms = n;
   }
   return n;
 }
@@ -214,14 +237,16 @@ struct TileChoice {
 //   epilogue per tile   = BN x {27 plain fp16 / RoPE, 32 fp32 reduce-add, 38 GELU (two warps per scheduler)} clk
 //   tiles run in rounds over the SMs (SM pairs); inside a CTA the epilogue of tile i overlaps the main loop of tile
 //   i+1, so a round costs max(main, epilogue) and the last tile's epilogue is exposed.
-// F5_BN_<n_out>=<bn>[p] overrides the choice (experiments).
+// Diagnostic build (make TRACE=1) only: F5_BN_<n_out>=<bn>[p] overrides the choice.
 TileChoice pick_tile(long long rows, int batches, int n_out, int k, int epi, int act) {
+#ifdef F5_TRACE
   char key[32];
   snprintf(key, sizeof key, "F5_BN_%d", n_out);
   if (const char* e = getenv(key)) {
     const int bn = atoi(e);
     if (bn == 64 || bn == 128 || bn == 192 || bn == 256) return {bn, strchr(e, 'p') != nullptr ? 1 : 0};
   }
+#endif
   const int sms = num_sms();
   const double kb = double((k + 63) / 64);
   const double epi_col = (act == F5_ACT_GELU_TANH || act == F5_ACT_GELU_ERF) ? 38.0 : (epi == F5_EPI_RESID ? 32.0 : 27.0);
@@ -300,6 +325,7 @@ int gemm_plan(GemmPlan* pl, const void* A, const void* W, const f5_gemm_args* a)
   p.pe_heads = a->pe_heads;
   p.conv_pad = a->conv_taps / 2;
   p.w_prefetch = a->weights_static ? 1 : 0;
+#ifdef F5_TRACE  // instrumented build only: kernel skip modes (wrong results) and the per-CTA timestamp trace
   {
     static int dbg = -1;
     if (dbg < 0) {
@@ -316,6 +342,7 @@ int gemm_plan(GemmPlan* pl, const void* A, const void* W, const f5_gemm_args* a)
     p.dbg_ts = trace;
     g_trace = trace;
   }
+#endif
   int rc;
   if (conv) {
     if (a->n_out % 64 || a->lda < a->n_out) {

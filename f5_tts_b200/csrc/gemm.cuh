@@ -26,6 +26,14 @@
 
 namespace f5 {
 
+// Diagnostic kernel modes (skip loads / MMAs / epilogue: WRONG results, timing decomposition only) exist in the
+// instrumented build (make TRACE=1) and nowhere else.
+#ifdef F5_TRACE
+#define F5_DBG(p, mode) ((p).dbg_mode == (mode))
+#else
+#define F5_DBG(p, mode) false
+#endif
+
 constexpr uint32_t kEpiChunkBytes = kBM * 128;  // 128 rows x 128 B (64 fp16 or 32 fp32 columns)
 constexpr int kEpiBufs = 2;                     // one staging buffer per epilogue column group
 
@@ -40,56 +48,6 @@ template <int BN, int STAGES, bool PAIR = false>
 constexpr size_t gemm_smem_bytes() {
   return size_t(STAGES) * (kBM * kBK * 2 + (PAIR ? BN / 2 : BN) * kBK * 2) + kEpiBufs * kEpiChunkBytes /*epilogue staging*/ +
          1024 /*align slack*/ + 256 /*barriers*/ + 2048 /*bias + gate staging*/;
-}
-
-// Values of one 32-column chunk of one accumulator row after bias / RoPE / activation (no store).
-template <int EPI, int ACT>
-__device__ __forceinline__ void epilogue_values(const GemmParams& p, const uint32_t (&r)[32], int nc, int pos,
-                                                float (&v)[32]) {
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (p.bias != nullptr) {
-      if (nc + 4 * i + 3 < p.n_out) b = __ldg(reinterpret_cast<const float4*>(p.bias + nc) + i);
-      else {
-        if (nc + 4 * i + 0 < p.n_out) b.x = __ldg(p.bias + nc + 4 * i + 0);
-        if (nc + 4 * i + 1 < p.n_out) b.y = __ldg(p.bias + nc + 4 * i + 1);
-        if (nc + 4 * i + 2 < p.n_out) b.z = __ldg(p.bias + nc + 4 * i + 2);
-      }
-    }
-    v[4 * i + 0] = __uint_as_float(r[4 * i + 0]) + b.x;
-    v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + b.y;
-    v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + b.z;
-    v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + b.w;
-  }
-  if (EPI == EPI_QKV_ROPE) {
-    const int sec = nc / p.inner;
-    const int head = (nc % p.inner) / 64;
-    if (sec < 2 && head < p.pe_heads) {
-      const int pair0 = (nc % 64) / 2;
-      const float4* cs = reinterpret_cast<const float4*>(p.rope_cos + (long long)pos * 32 + pair0);
-      const float4* sn = reinterpret_cast<const float4*>(p.rope_sin + (long long)pos * 32 + pair0);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float4 c4 = __ldg(cs + i), s4 = __ldg(sn + i);
-        const float cc[4] = {c4.x, c4.y, c4.z, c4.w}, ss[4] = {s4.x, s4.y, s4.z, s4.w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float x0 = v[8 * i + 2 * j], x1 = v[8 * i + 2 * j + 1];
-          v[8 * i + 2 * j] = x0 * cc[j] - x1 * ss[j];
-          v[8 * i + 2 * j + 1] = x1 * cc[j] + x0 * ss[j];
-        }
-      }
-    }
-  }
-  if (ACT != ACT_NONE) {
-#pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      if (ACT == ACT_GELU_TANH) v[i] = gelu_tanh(v[i]);
-      if (ACT == ACT_GELU_ERF) v[i] = gelu_erf(v[i]);
-      if (ACT == ACT_MISH) v[i] = mish(v[i]);
-    }
-  }
 }
 
 // fused epilogue for one 32-column chunk of one accumulator row
@@ -315,7 +273,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       };
       // weights of the first tile's first k-blocks: in flight before the dependency wait (slots are free at start)
       uint32_t pre = 0;
-      if (cta_id < num_tiles && p.dbg_mode != 1 && p.w_prefetch) {
+      if (cta_id < num_tiles && !F5_DBG(p, 1) && p.w_prefetch) {
         pre = uint32_t(p.num_kb < STAGES ? p.num_kb : STAGES);
         for (uint32_t kb = 0; kb < pre; ++kb) {
           arm(int(kb));
@@ -332,7 +290,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const uint32_t ph = (it / STAGES) & 1;
           if (it >= pre) {
             mbar_wait(&empty[s], ph ^ 1);
-            if (p.dbg_mode == 1) {
+            if (F5_DBG(p, 1)) {
               mbar_arrive(&full[s]);
               continue;
             }
@@ -367,7 +325,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const uint64_t bdesc = make_smem_desc_sw128(smem_u32(sB + s * B_BYTES));
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k) {
-            if (p.dbg_mode == 2) break;
+            if (F5_DBG(p, 2)) break;
             // +32 bytes (16 fp16) along K inside the 128B swizzle atom = +2 in the (addr >> 4) field
             if (PAIR) tc_mma_ss_pair(tmem_acc, adesc + uint64_t(k * 2), bdesc + uint64_t(k * 2), idesc, (kb | k) != 0);
             else tc_mma_ss(tmem_acc, adesc + uint64_t(k * 2), bdesc + uint64_t(k * 2), idesc, (kb | k) != 0);
@@ -393,7 +351,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int et = int(threadIdx.x) - 64;                 // 0 .. ETH-1
     const bool issuer = (et == eg * 128);                 // owns this group's bulk stores
     const int bar_a = 1 + 2 * eg, bar_b = 2 + 2 * eg;     // named barriers of this column group (128 threads)
-    uint8_t* sbuf = sC + eg * kEpiChunkBytes;             // one staging buffer per group (values wait in registers)
+    // Staging buffers: two column groups own one buffer each; a single group (EG = 1) uses BOTH as a ring, so the bulk
+    // store of chunk c reads its buffer while chunk c + 1 is already being written into the other one.
+    uint32_t cc = 0;                                      // running chunk counter of this group (EG = 1 ring index)
     const float* gate = nullptr;
     if (EPI == EPI_RESID && p.gate != nullptr)
       gate = p.gate + (p.step_ptr ? (long long)(*p.step_ptr) : 0) * p.gate_step_stride;
@@ -458,7 +418,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           tmem_ld32(tmem_acc + uint32_t(c * 32), r);
           tmem_ld_wait();
           const int nc = n0 + c * 32;
-          if (row_ok && nc < p.n_out && p.dbg_mode != 3) epilogue_chunk<EPI, ACT>(p, r, nc, grow, pos, valid, gate);
+          if (row_ok && nc < p.n_out && !F5_DBG(p, 3)) epilogue_chunk<EPI, ACT>(p, r, nc, grow, pos, valid, gate);
         }
       } else {
         // staged: 32-column pieces -> 128-byte row chunks in swizzled smem -> bulk TMA store / reduce-add.
@@ -540,7 +500,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 for (int j = 0; j < 16; ++j) st[sub * 16 + j] = valid ? pack_half2(v[2 * j], v[2 * j + 1]) : 0u;
               }
             }
-            if (issuer) tma_store_wait_read<0>();  // the group's previous bulk store has read the staging buffer
+            uint8_t* sbuf = sC + (EG == 2 ? uint32_t(eg) : (cc & 1u)) * kEpiChunkBytes;
+            ++cc;
+            if (issuer) {  // the bulk store that last read THIS buffer has finished reading it
+              if (EG == 2) tma_store_wait_read<0>();
+              else tma_store_wait_read<1>();
+            }
             named_bar_sync(bar_a, 128);
             uint8_t* srow = sbuf + erow * 128;
 #pragma unroll
@@ -549,7 +514,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                   make_uint4(st[4 * j], st[4 * j + 1], st[4 * j + 2], st[4 * j + 3]);
             fence_proxy_async_smem();
             named_bar_sync(bar_b, 128);
-            if (issuer && p.dbg_mode != 3) {
+            if (issuer && !F5_DBG(p, 3)) {
               const int c0 = n0 + ch * (32 * PPC);
               if (c0 < p.n_out) {
                 if (EPI == EPI_RESID) tma_reduce_add_3d(&tmC, sbuf, c0, m0, bz);

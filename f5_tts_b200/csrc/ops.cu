@@ -21,12 +21,8 @@ int run_row_norm(int mode, const NormParams& p, cudaStream_t s) {
   }
   // warps (= rows) per block: small blocks fit next to a still-running GEMM CTA (register file), so more of them are
   // resident with their modulation rows prefetched when the producer finishes
-  static int wpb = 0;
-  if (wpb == 0) {
-    const char* e = getenv("F5_NORM_WARPS");
-    wpb = e ? atoi(e) : 4;  // cfg2 on B200: 55.17 / 54.91 / 54.83 ms per utterance with 8 / 4 / 2
-    if (wpb != 2 && wpb != 4 && wpb != 8) wpb = 4;
-  }
+  // cfg2 on B200: 55.17 / 54.91 / 54.83 ms per utterance with 8 / 4 / 2 warps per block
+  constexpr int wpb = 4;
   PdlLaunch L(dim3((p.rows + wpb - 1) / wpb), dim3(32 * wpb), 0, s);
   cudaError_t ce;
   if (mode == 0) ce = cudaLaunchKernelEx(&L.cfg, row_norm_kernel<0>, p);

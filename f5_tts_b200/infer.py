@@ -70,10 +70,38 @@ def get_tokenizer(dataset_name: str, tokenizer: str = "custom"):
     return vocab, len(vocab)
 
 
+_RE_HAN_DEFAULT = re.compile(r"([\u4E00-\u9FD5a-zA-Z0-9+#&\._%\-]+)")  # jieba: blocks that go through the word graph
+_RE_SKIP_DEFAULT = re.compile(r"(\r\n|\s)")                            # jieba: separators kept between blocks
+_RE_FINALSEG_SKIP = re.compile(r"([a-zA-Z0-9]+(?:\.\d+)?%?)")           # jieba.finalseg: latin / number runs
+
+
+def _segment_no_chinese(text: str) -> list[str]:
+    """Segmentation jieba's `cut(text, HMM=True)` (and its Rust port rjieba, model/utils.py:160) produces for text WITHOUT
+    Chinese characters, restated from jieba's published algorithm (jieba/__init__.py `cut` / `__cut_DAG`,
+    jieba/finalseg `cut`; the package is absent from this image): the text is split into blocks of
+    [han letters digits + # & . _ % -]; such a block is unknown to the dictionary, so it goes to finalseg, which
+    splits it into latin / number runs — a decimal part and a trailing % stay attached ("3.14", "50%") — and the
+    characters between them; everything else is emitted whitespace by whitespace, character by character.
+    Not covered: the handful of ASCII entries of jieba's dictionary ("C++", "AT&T"), which jieba keeps whole."""
+    out: list[str] = []
+    for blk in _RE_HAN_DEFAULT.split(text):
+        if not blk:
+            continue
+        if _RE_HAN_DEFAULT.fullmatch(blk):
+            out.extend(x for x in _RE_FINALSEG_SKIP.split(blk) if x)
+        else:
+            for x in _RE_SKIP_DEFAULT.split(blk):
+                if _RE_SKIP_DEFAULT.fullmatch(x):
+                    out.append(x)
+                else:
+                    out.extend(x)
+    return out
+
+
 def convert_char_to_pinyin(text_list, polyphone=True):
-    """model/utils.py:148-185.  Non-Chinese text follows the reference exactly (whitespace rule included); Chinese
-    characters need jieba + pypinyin, which this image lacks — then a clear error is raised instead of silently
-    producing different tokens."""
+    """model/utils.py:148-185.  With rjieba + pypinyin installed this is the reference's function line for line; this
+    image has neither, so non-Chinese text is segmented by `_segment_no_chinese` (jieba's algorithm restated — decimals
+    and quoted words included) and Chinese text raises a clear error instead of silently producing different tokens."""
     trans = str.maketrans({";": ",", "“": '"', "”": '"', "‘": "'", "’": "'"})
     try:
         import rjieba
@@ -82,7 +110,7 @@ def convert_char_to_pinyin(text_list, polyphone=True):
         rjieba = None
 
     def is_chinese(c):
-        return "㄀" <= c <= "鿿"
+        return "\u3100" <= c <= "\u9fff"
 
     out = []
     for text in text_list:
@@ -91,7 +119,7 @@ def convert_char_to_pinyin(text_list, polyphone=True):
         if rjieba is None:
             if any(is_chinese(c) for c in text):
                 raise RuntimeError("Chinese text needs the rjieba + pypinyin packages (text front-end, out of scope)")
-            segs = re.findall(r"[A-Za-z0-9']+|[^A-Za-z0-9']", text)  # jieba splits latin words / single symbols alike
+            segs = _segment_no_chinese(text)
         else:
             segs = rjieba.cut(text)
         for seg in segs:

@@ -193,7 +193,8 @@ class _Backbone(nn.Module):
         _attach(self, "rotary_embed.inv_freq", inv_freq, buffer=True)
         self._engine_lock = threading.Lock()
         self._engine_state = None
-        self._tls = threading.local()
+        self._ws_lock = threading.Lock()
+        self._ws_free: dict = {}  # (device, stream) -> [uint8 tensors] not in use by a sample() call
 
     # -- engine management ------------------------------------------------------------------------------------
     def _fingerprint(self):
@@ -226,13 +227,23 @@ class _Backbone(nn.Module):
         """Text embeddings are recomputed inside every engine call; nothing is cached across calls."""
         return None
 
-    def workspace(self, nbytes: int, device) -> torch.Tensor:
-        """Per-thread scratch (the reference samples from a ThreadPoolExecutor, utils_infer.py:540-541)."""
-        ws = getattr(self._tls, "ws", None)
-        if ws is None or ws.numel() < nbytes or ws.device != torch.device(device):
-            ws = torch.empty(int(nbytes * 1.05) + 4096, dtype=torch.uint8, device=device)
-            self._tls.ws = ws
-        return ws
+    def _ws_acquire(self, nbytes: int, device, stream: int) -> torch.Tensor:
+        """Scratch for one engine call, from a pool keyed on (device, stream).  Concurrent sample() calls (the reference
+        samples from a ThreadPoolExecutor, utils_infer.py:540-541) each hold their own buffer; a finished call returns
+        it, so the next call — from any thread — reuses the same address and hits the engine's CUDA-graph cache (the
+        graph is keyed on the workspace address).  Reuse is stream-ordered, hence the stream in the key."""
+        key = (torch.device(device), int(stream))
+        with self._ws_lock:
+            free = self._ws_free.setdefault(key, [])
+            for i, ws in enumerate(free):
+                if ws.numel() >= nbytes:
+                    return free.pop(i)
+            free.clear()  # too small for the current shapes: let them go
+        return torch.empty(int(nbytes * 1.05) + 4096, dtype=torch.uint8, device=device)
+
+    def _ws_release(self, ws: torch.Tensor, device, stream: int) -> None:
+        with self._ws_lock:
+            self._ws_free.setdefault((torch.device(device), int(stream)), []).append(ws)
 
     def run(self, y, step_cond, text, t_grid, duration, cfg_strength, trajectory=None, v_out=None, use_graph=True):
         """One engine call = len(t_grid)-1 Euler steps.  All tensors on the CUDA device, fp32 / int64 / int32."""
@@ -243,7 +254,8 @@ class _Backbone(nn.Module):
         assert y.is_contiguous() and step_cond.is_contiguous() and text.is_contiguous()
         assert y.dtype == torch.float32 and step_cond.dtype == torch.float32 and text.dtype == torch.int64
         need = L.f5_sample_workspace_bytes(st["handle"], B, N, steps, float(cfg_strength))
-        ws = self.workspace(need, y.device)
+        stream = torch.cuda.current_stream(y.device).cuda_stream
+        ws = self._ws_acquire(need, y.device, stream)
         tg = (C.c_float * (steps + 1))(*[float(v) for v in t_grid])
         a = _lib.SampleArgs()
         a.B, a.N, a.nt, a.steps = B, N, text.shape[1], steps
@@ -254,9 +266,11 @@ class _Backbone(nn.Module):
         a.trajectory = trajectory.data_ptr() if trajectory is not None else None
         a.use_graph = 1 if use_graph else 0
         a.v_out = v_out.data_ptr() if v_out is not None else None
-        stream = torch.cuda.current_stream(y.device).cuda_stream
-        with torch.cuda.device(y.device):
-            _lib.check(L.f5_sample(st["handle"], C.byref(a), ws.data_ptr(), ws.numel(), stream), "f5_sample")
+        try:
+            with torch.cuda.device(y.device):
+                _lib.check(L.f5_sample(st["handle"], C.byref(a), ws.data_ptr(), ws.numel(), stream), "f5_sample")
+        finally:
+            self._ws_release(ws, y.device, stream)
 
     def sample_flops(self, B, N, steps, cfg_strength) -> float:
         return float(_lib.lib().f5_sample_flops(self.engine()["handle"], B, N, steps, float(cfg_strength)))
@@ -409,7 +423,13 @@ class CFM(nn.Module):
             duration = torch.full((batch,), duration, device=device, dtype=torch.long)
         duration = torch.maximum(torch.maximum((text != -1).sum(dim=-1), lens) + 1, duration)
         duration = duration.clamp(max=max_duration)
-        n_frames = int(duration.amax())  # the one host sync the reference also has (cfm.py:139)
+        # the one host sync the reference also has (cfm.py:139); the largest token id rides along so that an id outside
+        # the embedding table raises here, like the reference's nn.Embedding does (dit.py:103), instead of being read
+        # out of bounds on the device
+        n_frames, max_id = torch.stack([duration.amax(), text.amax().to(duration.dtype)]).tolist()
+        if max_id >= self.transformer.text_num_embeds:
+            raise IndexError(f"text token id {max_id} is outside the embedding table "
+                             f"(text_num_embeds = {self.transformer.text_num_embeds})")
 
         if duplicate_test:
             test_cond = F.pad(cond, (0, 0, cond_seq_len, n_frames - 2 * cond_seq_len), value=0.0)

@@ -13,6 +13,8 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
     config.addinivalue_line("markers", "slow: longer CPU test")
+    config.addinivalue_line("markers", "fullsize: GPU parity at the real BASELINE.json sizes; the CPU oracle leg takes "
+                                       "about a minute per test on the box's host cores")
 
 
 @pytest.fixture(scope="session")
@@ -28,7 +30,7 @@ def _gpu_test_deadline(request):
         return
     import faulthandler
 
-    faulthandler.dump_traceback_later(240, exit=True)
+    faulthandler.dump_traceback_later(900 if request.node.get_closest_marker("fullsize") else 240, exit=True)
     try:
         yield
     finally:

@@ -221,3 +221,22 @@ def test_load_vocoder_local_layout(tmp_path):
         infer.load_vocoder("bigvgan", is_local=True, local_path=str(tmp_path), device="cpu")
     with pytest.raises(Exception):  # decode has no CPU path
         voc.decode(torch.zeros(1, 100, 8))
+
+
+def test_segmentation_without_jieba_follows_jieba_rules():
+    """the no-rjieba fallback must tokenise like jieba (HMM mode) for non-Chinese text — decimals and
+    percentages stay whole, quotes after punctuation get no space (model/utils.py:148-185 downstream of rjieba.cut)."""
+    seg = infer._segment_no_chinese
+    assert seg("pi is 3.14, v2.10 at 50% off.") == ["pi", " ", "is", " ", "3.14", ",", " ", "v2.10", " ", "at", " ", "50%",
+                                                     " ", "off", "."]
+    assert seg("hello.'quote' ok") == ["hello", ".", "'", "quote", "'", " ", "ok"]
+    assert seg("a-b_c") == ["a", "-", "b", "_", "c"]
+    conv = lambda t: "".join(infer.convert_char_to_pinyin([t])[0])  # noqa: E731
+    assert conv("pi is 3.14.") == "pi is 3.14."          # not "3. 14"
+    assert conv("hello.'quote'") == "hello.'quote'"      # no space between the punctuation and the quote
+    assert conv("say:hi") == "say:hi" and conv("ab,cd") == "ab, cd"  # utils.py:172-174: space before a word unless after " :'\""
+    try:
+        import rjieba  # noqa: F401
+    except Exception:  # noqa: BLE001
+        with pytest.raises(RuntimeError):
+            infer.convert_char_to_pinyin(["你好"])
