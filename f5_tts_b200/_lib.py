@@ -27,6 +27,9 @@ class GemmArgs(C.Structure):
         ("gate", c_void_p), ("step_ptr", c_void_p), ("gate_step_stride", c_ll), ("row_len", c_void_p),
         ("seq", c_int), ("rope_cos", c_void_p), ("rope_sin", c_void_p), ("inner", c_int), ("pe_heads", c_int),
         ("weights_static", c_int),
+        ("norm_x", c_void_p), ("norm_mode", c_int), ("norm_a", c_void_p), ("norm_b", c_void_p),
+        ("norm_step_stride", c_ll), ("norm_counters", c_void_p), ("norm_eps", c_float),
+        ("skip_padded_tiles", c_int),
     ]
 
 
@@ -72,7 +75,7 @@ class SampleArgs(C.Structure):
         ("B", c_int), ("N", c_int), ("nt", c_int), ("steps", c_int),
         ("text", c_void_p), ("step_cond", c_void_p), ("y", c_void_p), ("duration", c_void_p),
         ("t", C.POINTER(c_float)), ("cfg_strength", c_float), ("trajectory", c_void_p), ("use_graph", c_int),
-        ("v_out", c_void_p),
+        ("v_out", c_void_p), ("exact_varlen", c_int),
     ]
 
 

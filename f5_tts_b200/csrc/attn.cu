@@ -1,11 +1,38 @@
 // Host side of the tcgen05 attention kernel + C entry point f5_attention.
 #include "attn.cuh"
-#include "attn_splitkv.cuh"
 #include "internal.h"
 
 #include <cstdlib>
 namespace f5 {
 static long long* g_attn_trace = nullptr;
+
+// The production library carries ONE kernel.  The instrumented build (make TRACE=1) also instantiates other MUFU / FMA
+// splits of the exponentials (F5_ATTN_POLY = pairs of every 8 on the FMA pipe) and reads F5_ATTN_TURNSTILE, for A/B
+// timing with tools/attn_bench.py.
+#ifdef F5_TRACE
+static int trace_poly() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("F5_ATTN_POLY");
+    v = e ? atoi(e) : kPolyOf8;
+  }
+  return v;
+}
+#endif
+
+typedef void (*AttnKernel)(const CUtensorMap, const AttnParams);
+static AttnKernel attn_kernel() {
+#ifdef F5_TRACE
+  switch (trace_poly()) {
+    case 0: return attn_fwd_tcgen05_kernel<0>;
+    case 2: return attn_fwd_tcgen05_kernel<2>;
+    case 4: return attn_fwd_tcgen05_kernel<4>;
+    case 5: return attn_fwd_tcgen05_kernel<5>;
+    default: break;
+  }
+#endif
+  return attn_fwd_tcgen05_kernel<kPolyOf8>;
+}
 
 int attn_plan(AttnPlan* pl, const void* qkv, void* out, int batches, int seq, int heads, const int* kv_len,
               float scale) {
@@ -24,26 +51,16 @@ int attn_plan(AttnPlan* pl, const void* qkv, void* out, int batches, int seq, in
   pl->p.kv_len = kv_len;
   pl->p.scale_log2 = scale * 1.4426950408889634f;
   pl->p.out = reinterpret_cast<__half*>(out);
+  pl->p.turnstile = 1;
+  pl->p.dbg_ts = nullptr;
+#ifdef F5_TRACE
   {
     static int ts = -1;
     if (ts < 0) {
       const char* e = getenv("F5_ATTN_TURNSTILE");
-      ts = e ? atoi(e) : 1;  // measured: 22.6 us (on) vs 24.4 us (off) at Be=2, seq=938
+      ts = e ? atoi(e) : 1;
     }
     pl->p.turnstile = ts;
-    static int var = -1;
-    if (var < 0) {
-      const char* e = getenv("F5_ATTN_VARIANT");
-      var = (e && atoi(e) == 6) ? 6 : 3;  // 6: experimental split-KV kernel (parity-green on B200, not timed yet)
-    }
-    pl->p.variant = var;
-    if (var == 6) {
-      rc = encode_tmap_f16(&pl->tm_kv64, qkv, (uint64_t)3 * inner, (uint64_t)seq, (uint64_t)batches, (uint64_t)3 * inner * 2,
-                           (uint64_t)seq * 3 * inner * 2, 64, 64, 3);
-      if (rc) return rc;
-    }
-  }
-  {
     static long long* trace = nullptr;
     static int want = -1;
     if (want < 0) {
@@ -53,38 +70,33 @@ int attn_plan(AttnPlan* pl, const void* qkv, void* out, int batches, int seq, in
     pl->p.dbg_ts = trace;
     g_attn_trace = trace;
   }
+#endif
   pl->grid = dim3((seq + 2 * kAttnBQ - 1) / (2 * kAttnBQ), heads, batches);
   return 0;
 }
 
-int attn_configure() {
-  if (int rc = check_cuda(cudaFuncSetAttribute(attn_fwd_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               (int)kAttnSmem),
+static int attn_configure_one(AttnKernel k) {
+  if (int rc = check_cuda(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAttnSmem),
                           "cudaFuncSetAttribute(attn smem)"))
     return rc;
-  cudaFuncSetAttribute(attn_fwd_tcgen05_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   return 0;
+}
+
+int attn_configure() {
+#ifdef F5_TRACE
+  if (int rc = attn_configure_one(attn_fwd_tcgen05_kernel<0>)) return rc;
+  if (int rc = attn_configure_one(attn_fwd_tcgen05_kernel<2>)) return rc;
+  if (int rc = attn_configure_one(attn_fwd_tcgen05_kernel<4>)) return rc;
+  if (int rc = attn_configure_one(attn_fwd_tcgen05_kernel<5>)) return rc;
+#endif
+  return attn_configure_one(attn_fwd_tcgen05_kernel<kPolyOf8>);
 }
 
 int attn_run(const AttnPlan& pl, cudaStream_t s) {
   if (int rc = configure_kernels()) return rc;
-  if (pl.p.variant == 6) {
-    static int configured = 0;  // the experimental kernel is configured only when it is asked for
-    if (!configured) {
-      if (int rc = check_cuda(cudaFuncSetAttribute(attn_fwd_splitkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                   (int)kSkvSmem),
-                              "cudaFuncSetAttribute(split-KV attn smem)"))
-        return rc;
-      cudaFuncSetAttribute(attn_fwd_splitkv_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-      configured = 1;
-    }
-    PdlLaunch L(pl.grid, dim3(kSkvThreads), kSkvSmem, s);
-    if (int rc = check_cuda(cudaLaunchKernelEx(&L.cfg, attn_fwd_splitkv_kernel, pl.tm, pl.tm_kv64, pl.p), "split-KV attention launch"))
-      return rc;
-  } else {
-    PdlLaunch L(pl.grid, dim3(kAttnThreads), kAttnSmem, s);
-    if (int rc = check_cuda(cudaLaunchKernelEx(&L.cfg, attn_fwd_tcgen05_kernel, pl.tm, pl.p), "attention launch")) return rc;
-  }
+  PdlLaunch L(pl.grid, dim3(kAttnThreads), kAttnSmem, s);
+  if (int rc = check_cuda(cudaLaunchKernelEx(&L.cfg, attn_kernel(), pl.tm, pl.p), "attention launch")) return rc;
   count_launch();
   return check_launch("attn_fwd_tcgen05_kernel launch");
 }

@@ -173,6 +173,16 @@ __global__ void mask_rows_kernel(float* x, const uint8_t* filler, int BN, int ro
   for (int c = threadIdx.x; c < C; c += blockDim.x) x[(long long)row * C + c] = 0.f;
 }
 
+// rows at or past the valid length of their sample are zeroed: x [variants * B, N, C], valid_len [B]
+template <typename T>
+__global__ void mask_rows_len_kernel(T* x, const int* valid_len, int B, int N, int rows, int C) {
+  const int row = blockIdx.x;
+  if (row >= rows) return;
+  const int b = (row / N) % B, n = row % N;
+  if (n < valid_len[b]) return;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) x[(long long)row * C + c] = T(0.f);
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // GRN (modules.py:236-245): Gx[b,c] = ||g[b,:,c]||_2 over the SEQUENCE; Nx = Gx / (mean_c Gx + 1e-6);
 // g <- gamma * (g * Nx) + beta + g.   g fp16 [B, N, C].

@@ -42,11 +42,14 @@ struct Layout {
   // common
   int* step_ptr;
   SampleIo* io;     // caller tensors + cfg scale of THIS call, read by the step kernels through the workspace
+  int* norm_ctr;    // [2 * depth][ceil(M1 / 128)] row counters of the GEMMs that normalise their own A operand
+  int norm_blocks;  // ceil(M1 / 128)
   float* dt;
   float* t_dev;
   float *rope_cos, *rope_sin;
   int* row_len;     // [Be] or unused
   int* kv_len;      // [Be] or unused
+  int* frame_len;   // [Be] valid mel frames per sample (row_len without the UNetT time token)
   int* valid_len;   // [B]
   float *tfeat, *th1, *temb;
   __half* temb_silu;
@@ -86,7 +89,7 @@ struct GraphHolder {
 };
 struct GraphKey {
   const void* ws;
-  int B, N, steps, packed, masked;
+  int B, N, steps, packed, masked;  // masked: 0 = no lengths, 1 = lengths (reference batched semantics), 2 = exact_varlen
   bool operator==(const GraphKey& o) const {
     return ws == o.ws && B == o.B && N == o.N && steps == o.steps && packed == o.packed && masked == o.masked;
   }
@@ -119,12 +122,15 @@ static void plan_layout(const f5_engine* e, Layout& L, void* ws, int B, int N, i
   const int D = A.dim, Td = A.text_dim, F = A.ff_inner;
   L.step_ptr = bp.take<int>(64);
   L.io = bp.take<SampleIo>(1);
+  L.norm_blocks = (int)((L.M1 + 127) / 128);
+  L.norm_ctr = bp.take<int>((size_t)2 * A.depth * L.norm_blocks);
   L.dt = bp.take<float>(steps + 1);
   L.t_dev = bp.take<float>(steps + 1);
   L.rope_cos = bp.take<float>((size_t)L.seq * 32);
   L.rope_sin = bp.take<float>((size_t)L.seq * 32);
   L.row_len = bp.take<int>(L.Be);
   L.kv_len = bp.take<int>(L.Be);
+  L.frame_len = bp.take<int>(L.Be);
   L.valid_len = bp.take<int>(B);
   L.tfeat = bp.take<float>((size_t)steps * 256);
   L.th1 = bp.take<float>((size_t)steps * D);
@@ -273,6 +279,8 @@ int build_step_plans(f5_engine* e, const Layout& L, const f5_sample_args* sa, St
   const int D = A.dim, F = A.ff_inner, inner = e->inner;
   const bool dit = A.backbone == 0;
   const bool masked = sa->duration != nullptr;
+  const bool strict = masked && sa->exact_varlen;  // every sample exactly as if alone in the batch (f5_sample_args)
+  const bool mask_in = (dit && masked) || strict;  // input projection / conv position embedding see per-sample lengths
   const int pe_heads = A.pe_attn_head < 0 ? A.heads : A.pe_attn_head;
   const long long modS = e->modW;
 
@@ -283,7 +291,8 @@ int build_step_plans(f5_engine* e, const Layout& L, const f5_sample_args* sa, St
     a.out16b = L.h0h;
     a.ldo = D;
     a.seq = L.N;
-    a.row_len = (dit && masked) ? L.row_len : nullptr;
+    a.row_len = mask_in ? L.frame_len : nullptr;
+    a.skip_padded_tiles = (mask_in && (A.attn_mask_enabled || strict)) ? 1 : 0;
     RC(gemm_plan(&P.proj, L.xin, W.proj_w, &a));
   }
   for (int c = 0; c < 2; ++c) {  // grouped conv position embedding
@@ -298,7 +307,8 @@ int build_step_plans(f5_engine* e, const Layout& L, const f5_sample_args* sa, St
     a.bias = W.conv_b[c];
     a.ldo = D;
     a.seq = L.N;
-    a.row_len = (dit && masked) ? L.row_len : nullptr;
+    a.row_len = mask_in ? L.frame_len : nullptr;
+    a.skip_padded_tiles = (mask_in && (A.attn_mask_enabled || strict)) ? 1 : 0;
     if (c == 0) {
       a.epi = F5_EPI_F16;
       a.out = L.c1;
@@ -315,16 +325,46 @@ int build_step_plans(f5_engine* e, const Layout& L, const f5_sample_args* sa, St
   P.ff2.resize(A.depth);
   P.skip.resize(A.depth);
   const int* rl = masked ? L.row_len : nullptr;
+  // Variable-length execution: in the reference's key-masked mode (attn_mask_enabled, modules.py:
+  // 513-518) padded rows influence nothing, so every GEMM / conv / attention tile that holds only padding is skipped.
+  // In the default "faithful" mode padded keys ARE attended and every row must be computed.
+  const int skip = (masked && (A.attn_mask_enabled || strict)) ? 1 : 0;
+  auto varlen = [&](f5_gemm_args& a) {
+    if (!skip) return;
+    a.row_len = L.row_len;
+    a.seq = L.seq;
+    a.skip_padded_tiles = 1;
+  };
+  // The row normalisation in front of the QKV and FF1 projections runs INSIDE those GEMMs (gemm.cuh: NORMA): x (fp32
+  // residual stream) -> L.a (fp16) by the GEMM's own epilogue warps, consumed 128-row block by 128-row block.
+  auto fuse_norm = [&](f5_gemm_args& a, int layer, int which) {
+    a.norm_x = L.x;
+    a.norm_eps = 1e-6f;
+    a.norm_counters = L.norm_ctr + (size_t)(2 * layer + which) * L.norm_blocks;
+    a.step_ptr = L.step_ptr;
+    if (dit) {
+      const float* m = L.mod + (size_t)layer * 6 * D + (which ? 3 * D : 0);  // shift, scale (modules.py:323)
+      a.norm_mode = 0;
+      a.norm_a = m + D;
+      a.norm_b = m;
+      a.norm_step_stride = modS;
+    } else {
+      a.norm_mode = 2;
+      a.norm_a = which ? W.layers[layer].g_ff : W.layers[layer].g_attn;
+      a.norm_step_stride = 0;
+    }
+  };
   for (int i = 0; i < A.depth; ++i) {
     const f5_layer_weights& lw = W.layers[i];
     if (!dit && lw.w_skip) {
       f5_gemm_args a = base_args(L.M1, D, 2 * D, 2 * D, 2 * D, 128, F5_EPI_F32, F5_ACT_NONE);
       a.out = L.x;
       a.ldo = D;
-      RC(gemm_plan(&P.skip[i], L.cat, lw.w_skip, &a));
+      RC(gemm_plan(&P.skip[i], L.cat, lw.w_skip, &a));  // (EPI_F32 direct-store path: not tile-skipped)
     }
     {
       f5_gemm_args a = base_args(L.M1, 3 * inner, D, D, D, kAutoTile, F5_EPI_QKV_ROPE, F5_ACT_NONE);
+      fuse_norm(a, i, 0);  // attn_norm (AdaLN: scale_msa, shift_msa / RMSNorm g) inside the QKV projection
       a.bias = lw.b_qkv;
       a.out = L.qkv;
       a.ldo = 3 * inner;
@@ -333,6 +373,7 @@ int build_step_plans(f5_engine* e, const Layout& L, const f5_sample_args* sa, St
       a.rope_sin = L.rope_sin;
       a.inner = inner;
       a.pe_heads = pe_heads;
+      varlen(a);
       RC(gemm_plan(&P.qkv[i], L.a, lw.w_qkv, &a));
     }
     {
@@ -347,13 +388,16 @@ int build_step_plans(f5_engine* e, const Layout& L, const f5_sample_args* sa, St
         a.step_ptr = L.step_ptr;
         a.gate_step_stride = modS;
       }
+      varlen(a);
       RC(gemm_plan(&P.oproj[i], L.ao, lw.w_out, &a));
     }
     {
       f5_gemm_args a = base_args(L.M1, F, D, D, D, kAutoTile, F5_EPI_F16, F5_ACT_GELU_TANH);
+      fuse_norm(a, i, 1);  // ff_norm (scale_mlp, shift_mlp / RMSNorm g) inside the first feed-forward projection
       a.bias = lw.b_ff1;
       a.out = L.g;
       a.ldo = F;
+      varlen(a);
       RC(gemm_plan(&P.ff1[i], L.a, lw.w_ff1, &a));
     }
     {
@@ -366,6 +410,7 @@ int build_step_plans(f5_engine* e, const Layout& L, const f5_sample_args* sa, St
         a.step_ptr = L.step_ptr;
         a.gate_step_stride = modS;
       }
+      varlen(a);
       RC(gemm_plan(&P.ff2[i], L.g, lw.w_ff2, &a));
     }
   }
@@ -377,7 +422,7 @@ int build_step_plans(f5_engine* e, const Layout& L, const f5_sample_args* sa, St
     RC(gemm_plan(&P.out_proj, L.a, W.out_w, &a));
   }
   P.attn.resize(1);
-  RC(attn_plan(&P.attn[0], L.qkv, L.ao, L.Be, L.seq, A.heads, (A.attn_mask_enabled && masked) ? L.kv_len : nullptr,
+  RC(attn_plan(&P.attn[0], L.qkv, L.ao, L.Be, L.seq, A.heads, skip ? L.kv_len : nullptr,
                1.0f / sqrtf((float)A.dim_head)));
   return 0;
 }
@@ -422,11 +467,7 @@ int run_step(f5_engine* e, const Layout& L, const f5_sample_args* sa, const Step
   if (!dit) RC(run_prepend_time_token(L.x, L.h0, L.temb, L.step_ptr, L.N, D, L.M1, s));
   const int half = A.depth / 2;
   for (int i = 0; i < A.depth; ++i) {
-    const f5_layer_weights& lw = e->w.layers[i];
-    if (dit) {
-      const float* m = L.mod + (size_t)i * 6 * D;
-      RC(norm_mod(e, L, L.x, L.M1, 0, m + D, m, true, s));  // scale_msa, shift_msa
-    } else {
+    if (!dit) {
       if (i < half) {
         RC(check_cuda(cudaMemcpyAsync(L.skips[i], L.x, sizeof(float) * L.M1 * D, cudaMemcpyDeviceToDevice, s),
                       "skip copy"));
@@ -434,18 +475,11 @@ int run_step(f5_engine* e, const Layout& L, const f5_sample_args* sa, const Step
         RC(run_concat_half(L.x, L.skips[A.depth - 1 - i], L.cat, L.M1, D, s));
         RC(gemm_run(P.skip[i], s));
       }
-      RC(norm_mod(e, L, L.x, L.M1, 2, lw.g_attn, nullptr, false, s));
     }
-    if (!diag_skip("qkv")) RC(gemm_run(P.qkv[i], s));
+    if (!diag_skip("qkv")) RC(gemm_run(P.qkv[i], s));  // attn_norm fused (NORMA)
     if (!diag_skip("attn")) RC(attn_run(P.attn[0], s));
     if (!diag_skip("out")) RC(gemm_run(P.oproj[i], s));
-    if (dit) {
-      const float* m = L.mod + (size_t)i * 6 * D;
-      RC(norm_mod(e, L, L.x, L.M1, 0, m + 4 * D, m + 3 * D, true, s));  // scale_mlp, shift_mlp
-    } else {
-      RC(norm_mod(e, L, L.x, L.M1, 2, lw.g_ff, nullptr, false, s));
-    }
-    if (!diag_skip("ff1")) RC(gemm_run(P.ff1[i], s));
+    if (!diag_skip("ff1")) RC(gemm_run(P.ff1[i], s));  // ff_norm fused (NORMA)
     if (!diag_skip("ff2")) RC(gemm_run(P.ff2[i], s));
   }
   if (dit) {
@@ -478,12 +512,14 @@ int run_prologue(f5_engine* e, const Layout& L, const f5_sample_args* sa, cudaSt
   const int D = A.dim, Td = A.text_dim, B = L.B, N = L.N, S = L.steps;
   const bool dit = A.backbone == 0;
   const bool masked = sa->duration != nullptr;
+  const bool strict = masked && sa->exact_varlen;
   // small host -> device control data (pageable source: cudaMemcpyAsync stages it before returning)
   std::vector<float> dt(S + 1, 0.f);
   for (int k = 0; k < S; ++k) dt[k] = sa->t[k + 1] - sa->t[k];
   RC(check_cuda(cudaMemcpyAsync(L.dt, dt.data(), sizeof(float) * (S + 1), cudaMemcpyHostToDevice, s), "dt h2d"));
   RC(check_cuda(cudaMemcpyAsync(L.t_dev, sa->t, sizeof(float) * (S + 1), cudaMemcpyHostToDevice, s), "t h2d"));
   RC(check_cuda(cudaMemsetAsync(L.step_ptr, 0, sizeof(int) * 64, s), "step memset"));
+  RC(check_cuda(cudaMemsetAsync(L.norm_ctr, 0, sizeof(int) * 2 * A.depth * L.norm_blocks, s), "norm counters"));
   SampleIo io{sa->y, sa->trajectory, sa->cfg_strength};
   RC(check_cuda(cudaMemcpyAsync(L.io, &io, sizeof(io), cudaMemcpyHostToDevice, s), "io h2d"));
   if (masked) {
@@ -496,7 +532,17 @@ int run_prologue(f5_engine* e, const Layout& L, const f5_sample_args* sa, cudaSt
     RC(check_cuda(cudaMemcpyAsync(L.row_len, rl.data(), sizeof(int) * L.Be, cudaMemcpyHostToDevice, s), "row_len"));
     RC(check_cuda(cudaMemcpyAsync(L.kv_len, rl.data(), sizeof(int) * L.Be, cudaMemcpyHostToDevice, s), "kv_len"));
     RC(check_cuda(cudaMemcpyAsync(L.valid_len, hd.data(), sizeof(int) * B, cudaMemcpyHostToDevice, s), "valid_len"));
+    std::vector<int> fl(L.Be);
+    for (int i = 0; i < L.Be; ++i) fl[i] = hd[i % B];
+    RC(check_cuda(cudaMemcpyAsync(L.frame_len, fl.data(), sizeof(int) * L.Be, cudaMemcpyHostToDevice, s), "frame_len"));
     RC(check_cuda(cudaStreamSynchronize(s), "len sync"));
+    if (A.attn_mask_enabled || sa->exact_varlen) {
+      // tile skipping leaves padded rows of these buffers unwritten for the whole call: the conv inputs must read as
+      // zero there (= the conv's padding), and q/k/v rows next to a sample's end are multiplied by P = 0 (must be finite)
+      RC(check_cuda(cudaMemsetAsync(L.h0h, 0, sizeof(__half) * L.M * D, s), "h0h clear"));
+      RC(check_cuda(cudaMemsetAsync(L.c1, 0, sizeof(__half) * L.M * D, s), "c1 clear"));
+      RC(check_cuda(cudaMemsetAsync(L.qkv, 0, sizeof(__half) * L.M1 * 3 * e->inner, s), "qkv clear"));
+    }
   }
   RC(run_rope_table(L.rope_cos, L.rope_sin, L.seq, 32, s));
   // time embedding for every grid point (modules.py:852-862)
@@ -547,12 +593,16 @@ int run_prologue(f5_engine* e, const Layout& L, const f5_sample_args* sa, cudaSt
     g1.out = L.tg;
     g1.ldo = 2 * Td;
     RC(f5_gemm(L.ta, W.text_blocks[i].pw1_w, &g1, s));
+    // exact_varlen: the sequence ends at the sample's own length — rows past it take no part in GRN's norm over the
+    // sequence (modules.py:243) and are cleared again after the block (= the zero padding a B = 1 call would see)
+    if (strict) RC(run_mask_rows_len_half(L.tg, L.valid_len, B, N, R2, 2 * Td, s));
     RC(run_grn(L.tg, L.sumsq, L.nx, W.text_blocks[i].grn_gamma, W.text_blocks[i].grn_beta, 2 * B, N, 2 * Td, s));
     f5_gemm_args g2 = base_args(R2, Td, 2 * Td, 2 * Td, 2 * Td, 64, F5_EPI_RESID, F5_ACT_NONE);
     g2.bias = W.text_blocks[i].pw2_b;
     g2.resid = L.tx;
     g2.ldo = Td;
     RC(f5_gemm(L.tg, W.text_blocks[i].pw2_w, &g2, s));
+    if (strict) RC(run_mask_rows_len(L.tx, L.valid_len, B, N, R2, Td, s));
   }
   if (A.conv_layers > 0 && A.text_mask_padding) RC(run_mask_rows(L.tx, L.filler, B * N, R2, Td, s));
   PackParams pp{};
@@ -604,7 +654,8 @@ extern "C" int f5_sample(f5_engine* e, const f5_sample_args* sa, void* workspace
   }
   RC(run_prologue(e, L, sa, s));
   if (sa->use_graph) {
-    const GraphKey key{workspace, sa->B, sa->N, sa->steps, L.packed, sa->duration != nullptr ? 1 : 0};
+    const GraphKey key{workspace, sa->B, sa->N, sa->steps, L.packed,
+                       sa->duration == nullptr ? 0 : (sa->exact_varlen ? 2 : 1)};
     std::shared_ptr<GraphHolder> g;
     {
       std::lock_guard<std::mutex> lk(e->mu);

@@ -171,15 +171,146 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
   }
 }
 
+// ---- fused A-operand normalisation (NORMA kernels) -------------------------------------------------------------
+// The AdaLN / RMS row normalisation that precedes the QKV and FF1 projections used to be a kernel of its own between
+// two GEMMs: two grid-wide dependency hand-offs (~1.5 us each) around ~2 us of L2-latency-bound work, 44 times per NFE
+// step.  A NORMA GEMM does the normalisation itself: before their first tile, the epilogue warps of ALL its CTAs
+// normalise the rows of x (fp32, L2 resident) into the fp16 A buffer, block of 128 rows by block of 128 rows, and
+// publish per-block row counters (release); the TMA producer of a tile waits (acquire) only for the 128-row block it
+// is about to load and orders its async-proxy reads after the generic-proxy writes with fence.proxy.async.  Weight
+// tiles stream in meanwhile.  Counters are cumulative over the steps of one sample() call (target = rows x (step + 1)),
+// so a replayed CUDA graph needs no reset.
+__device__ __forceinline__ void norm_rows_phase(const GemmParams& p, int gw, int total_warps) {
+  const int lane = int(lane_id());
+  const int nv = p.norm_d >> 7;  // float4 per lane (norm_d multiple of 128, <= 1024)
+  const long long so = p.step_ptr ? (long long)(*p.step_ptr) * p.norm_step_stride : 0;
+  float4 ga[8], gb[8];
+  const float4* A4 = reinterpret_cast<const float4*>(p.norm_a + so);
+  const float4* B4 = p.norm_mode == 0 ? reinterpret_cast<const float4*>(p.norm_b + so) : nullptr;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if (i < nv) {
+      ga[i] = __ldg(A4 + i * 32 + lane);
+      if (p.norm_mode == 0) {
+        gb[i] = __ldg(B4 + i * 32 + lane);
+        ga[i].x += 1.f, ga[i].y += 1.f, ga[i].z += 1.f, ga[i].w += 1.f;
+      }
+    }
+  const float inv_d = 1.0f / float(p.norm_d);
+  float4 v[8];
+  int r = gw;
+  if (r < p.rows) {
+    const float4* xr = reinterpret_cast<const float4*>(p.norm_x + (long long)r * p.norm_d);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (i < nv) v[i] = xr[i * 32 + lane];
+  }
+  while (r < p.rows) {
+    const int rn = r + total_warps;
+    float4 vn[8];
+    if (rn < p.rows) {  // next row of this warp: in flight while the current one is reduced
+      const float4* xr = reinterpret_cast<const float4*>(p.norm_x + (long long)rn * p.norm_d);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (i < nv) vn[i] = xr[i * 32 + lane];
+    }
+    float s = 0.f, mean = 0.f, rstd;
+    if (p.norm_mode == 0) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (i < nv) s += v[i].x + v[i].y + v[i].z + v[i].w;
+      mean = warp_sum(s) * inv_d;
+      float q = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (i < nv) {
+          const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+          q += a * a + b * b + c * c + d * d;
+        }
+      rstd = rsqrtf(warp_sum(q) * inv_d + p.norm_eps);
+    } else {
+      float q = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (i < nv) q += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+      rstd = sqrtf(float(p.norm_d)) / fmaxf(sqrtf(warp_sum(q)), 1e-12f);
+    }
+    uint2* o = reinterpret_cast<uint2*>(p.norm_out + (long long)r * p.norm_d);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (i < nv) {
+        const float4 a = ga[i];
+        float4 y;
+        if (p.norm_mode == 0) {
+          const float4 b = gb[i];
+          y.x = (v[i].x - mean) * rstd * a.x + b.x;
+          y.y = (v[i].y - mean) * rstd * a.y + b.y;
+          y.z = (v[i].z - mean) * rstd * a.z + b.z;
+          y.w = (v[i].w - mean) * rstd * a.w + b.w;
+        } else {
+          y.x = v[i].x * rstd * a.x;
+          y.y = v[i].y * rstd * a.y;
+          y.z = v[i].z * rstd * a.z;
+          y.w = v[i].w * rstd * a.w;
+        }
+        o[i * 32 + lane] = make_uint2(pack_half2(y.x, y.y), pack_half2(y.z, y.w));
+      }
+    asm volatile("fence.proxy.async.global;" ::: "memory");  // generic-proxy writes -> visible to TMA (async proxy) reads
+    __syncwarp();
+    if (lane == 0) {
+      __threadfence();
+      atomicAdd(p.norm_ctr + (r >> 7), 1);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = vn[i];
+    r = rn;
+  }
+}
+
+// TMA producer side: the 128-row block `mblk` of the A buffer is complete for this step
+__device__ __forceinline__ void norm_wait_block(const GemmParams& p, int mblk, int epoch) {
+  if (mblk * kBM >= p.rows) return;  // tile past the end (zero-filled by TMA)
+  const int nrows = min(kBM, p.rows - mblk * kBM);
+  const int target = nrows * (epoch + 1);
+  const int* c = p.norm_ctr + mblk;
+  int v;
+  long long t0 = 0;
+  for (;;) {
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(c) : "memory");
+    if (v >= target) break;
+    if (t0 == 0) t0 = clock64();
+    if (clock64() - t0 > F5_SPIN_TIMEOUT_CYCLES) {
+      printf("f5: norm block wait timeout block %d mblk %d have %d want %d\n", blockIdx.x, mblk, v, target);
+      __trap();
+    }
+  }
+  asm volatile("fence.proxy.async.global;" ::: "memory");
+}
+
+// Packed / variable-length execution (reference masked mode modules.py:513-540): with skip_pad, a tile
+// whose rows ALL lie past the end of their sample is never loaded, multiplied or stored.  Every warp role evaluates the
+// same predicate, so the smem ring, the TMEM double buffer and the tile order stay in step.  m0 = first row of the
+// (pair-)tile, tm = its height; CONV: rows are per sample (bz), plain: rows are the flattened [samples x seq] axis.
+template <bool CONV>
+__device__ __forceinline__ bool tile_is_padding(const GemmParams& p, int m0, int tm, int bz) {
+  if (!p.skip_pad) return false;
+  if (CONV) return m0 >= p.row_len[bz];
+  const int last = min(m0 + tm, p.rows) - 1;
+  const int b0 = m0 / p.seq;
+  if (b0 != last / p.seq) return false;  // the tile reaches into the next sample, whose first rows are valid
+  return m0 - b0 * p.seq >= p.row_len[b0];
+}
+
 // PAIR = true: cta_group::2.  Two CTAs of a cluster (same TPC) compute one 256 x BN tile: each CTA stages its own 128
 // rows of A and HALF of the W tile (BN/2 rows), the leader CTA issues tcgen05.mma.cta_group::2 (M = 256) for both, and
 // each CTA's accumulator half lands in its own TMEM.  Shared-memory traffic per MMA cycle drops by 1/4 (BN = 256) —
 // the measured limiter of the single-CTA kernel (operand writes by TMA + reads by the tensor core > 128 B/clk).
-template <int BN, int STAGES, int EPI, int ACT, bool CONV, bool PAIR = false>
+template <int BN, int STAGES, int EPI, int ACT, bool CONV, bool PAIR = false, bool NORMA = false>
 __global__ void __launch_bounds__(gemm_threads(ACT), 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
   static_assert(!(PAIR && CONV), "the conv schedule is single-CTA");
+  static_assert(!(NORMA && CONV), "fused A normalisation is for plain GEMMs");
   constexpr int BNL = PAIR ? BN / 2 : BN;  // W rows staged by this CTA
   constexpr int TM = PAIR ? 2 * kBM : kBM;  // rows of one (pair-)tile
   constexpr uint32_t A_BYTES = kBM * kBK * 2;
@@ -281,10 +412,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
       }
       pdl_wait();
+      const int epoch = (NORMA && p.step_ptr) ? *p.step_ptr : 0;
       for (int t = cta_id; t < num_tiles; t += cta_step) {
         const int n0 = (t % tiles_n) * BN;
         const int m0 = ((t / tiles_n) % tiles_m) * TM + int(rank) * kBM;
         const int bz = t / (tiles_n * tiles_m);
+        if (tile_is_padding<CONV>(p, ((t / tiles_n) % tiles_m) * TM, TM, bz)) continue;
+        if (NORMA) norm_wait_block(p, m0 / kBM, epoch);  // the epilogue warps of all CTAs are producing this block
         for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
@@ -308,7 +442,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       // ===== MMA issuer (leader CTA only when PAIR) =====
       constexpr uint32_t idesc = make_idesc_f16(TM, BN, 0, 0);
       uint32_t it = 0, tl = 0;
-      for (int t = cta_id; t < num_tiles; t += cta_step, ++tl) {
+      for (int t = cta_id; t < num_tiles; t += cta_step) {
+        if (tile_is_padding<CONV>(p, ((t / tiles_n) % tiles_m) * TM, TM, t / (tiles_n * tiles_m))) continue;
         const uint32_t buf = tl & 1;
         mbar_wait(&acc_empty[buf], ((tl >> 1) & 1) ^ 1);  // epilogue drained this accumulator
         tc_fence_after();
@@ -335,6 +470,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         if (PAIR) tc_commit_pair(&acc_full[buf]);
         else tc_commit(&acc_full[buf]);
+        ++tl;
       }
 #ifdef F5_TRACE
       if (ts) ts[4] = clock64();  // all MMAs issued
@@ -354,6 +490,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // Staging buffers: two column groups own one buffer each; a single group (EG = 1) uses BOTH as a ring, so the bulk
     // store of chunk c reads its buffer while chunk c + 1 is already being written into the other one.
     uint32_t cc = 0;                                      // running chunk counter of this group (EG = 1 ring index)
+    if (NORMA) norm_rows_phase(p, int(blockIdx.x) * (ETH / 32) + (et >> 5), int(gridDim.x) * (ETH / 32));
     const float* gate = nullptr;
     if (EPI == EPI_RESID && p.gate != nullptr)
       gate = p.gate + (p.step_ptr ? (long long)(*p.step_ptr) : 0) * p.gate_step_stride;
@@ -361,10 +498,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #ifdef F5_TRACE
     long long t_accwait = 0;
 #endif
-    for (int t = cta_id; t < num_tiles; t += cta_step, ++tl) {
+    for (int t = cta_id; t < num_tiles; t += cta_step) {
       const int n0 = (t % tiles_n) * BN;
       const int m0 = ((t / tiles_n) % tiles_m) * TM + int(rank) * kBM;
       const int bz = t / (tiles_n * tiles_m);
+      if (tile_is_padding<CONV>(p, ((t / tiles_n) % tiles_m) * TM, TM, bz)) continue;
       const uint32_t buf = tl & 1;
       const int row_in_batch = m0 + q * 32 + int(lane_id());
       const bool row_ok = row_in_batch < p.rows;
@@ -528,6 +666,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       tc_fence_before();
       if (PAIR) mbar_arrive_cluster(mapa_u32(&acc_empty[buf], 0));  // the leader's MMA issuer owns the accumulator ring
       else mbar_arrive(&acc_empty[buf]);
+      ++tl;
     }
 #ifdef F5_TRACE
     if (ts && threadIdx.x == 64) ts[12] = clock64();

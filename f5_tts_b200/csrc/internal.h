@@ -50,14 +50,13 @@ struct GemmPlan {
   CUtensorMap tmA, tmB, tmC;
   GemmParams p;
   dim3 grid;
-  int bn, epi, act, conv, pair;
+  int bn, epi, act, conv, pair, norma;
 };
 int gemm_plan(GemmPlan* plan, const void* A, const void* W, const f5_gemm_args* a);
 int gemm_run(const GemmPlan& plan, cudaStream_t s);
 
 struct AttnPlan {
   CUtensorMap tm;
-  CUtensorMap tm_kv64;  // 64-row K / V boxes (experimental split-KV kernel only)
   AttnParams p;
   dim3 grid;
 };
@@ -80,6 +79,8 @@ int run_row_norm(int mode, const NormParams& p, cudaStream_t s);
 int run_dwconv7_ln(const DwConvLnParams& p, cudaStream_t s);
 int run_text_gather(const TextGatherParams& p, cudaStream_t s);
 int run_mask_rows(float* x, const uint8_t* filler, int BN, int rows, int C, cudaStream_t s);
+int run_mask_rows_len(float* x, const int* valid_len, int B, int N, int rows, int C, cudaStream_t s);
+int run_mask_rows_len_half(__half* x, const int* valid_len, int B, int N, int rows, int C, cudaStream_t s);
 constexpr int kGrnRows = 64;  // sequence rows per partial-sum block
 int run_grn(__half* g, float* partial, float* nx, const float* gamma, const float* beta, int B, int N, int C,
             cudaStream_t s);

@@ -34,7 +34,17 @@ struct GemmParams {
   int inner;     // heads * dim_head
   int pe_heads;  // heads that get rotary (q and k sections)
   int conv_pad;  // CONV: taps/2
+  int skip_pad;    // 1: 128-row (256 for CTA pairs) tiles whose rows all lie past their sample's row_len are not computed
   int w_prefetch;  // W tiles may be loaded before griddepcontrol.wait (weights are not produced by the predecessor)
+  // NORMA kernels: the A operand is produced by this kernel (row norm + modulation of norm_x), see gemm.cuh
+  const float* norm_x;      // fp32 [rows, norm_d]
+  __half* norm_out;         // fp16 [rows, norm_d] = the buffer tmA points at
+  const float* norm_a;      // mode 0: scale  mode 2: g      (+ step * norm_step_stride)
+  const float* norm_b;      // mode 0: shift
+  long long norm_step_stride;
+  int* norm_ctr;            // [ceil(rows / 128)] rows finished per 128-row block, cumulative over the steps of a sample() call
+  int norm_mode, norm_d;
+  float norm_eps;
   long long* dbg_ts;  // optional [gridDim.x][8] clock64/globaltimer trace (diagnostics; NULL in production)
   int dbg_mode;  // 0 normal; 1 = skip TMA loads, 2 = skip MMAs, 3 = skip epilogue math/stores (perf decomposition only)
 };
@@ -53,15 +63,14 @@ struct AttnParams {
   __half* out;        // [Be*seq, inner]
   long long* dbg_ts;  // optional [CTAs][16] phase-cycle trace (diagnostics; NULL in production)
   int turnstile;      // 1: serialise the exp2 loops of the two softmax warpgroups (ping-pong); 0: free-running
-  int variant;        // 3 = production kernel (attn.cuh); 6 = EXPERIMENTAL split-KV kernel (attn_splitkv.cuh, F5_ATTN_VARIANT=6; parity-green, untimed)
 };
 
-constexpr int kAttnThreads = 320;   // TMA warp + MMA warp + 2 softmax warpgroups
+constexpr int kAttnThreads = 384;   // producer warpgroup (TMA warp, MMA warp, 2 idle) + 2 softmax warpgroups
 constexpr int kAttnBQ = 128;        // rows per query tile (two tiles per CTA)
 constexpr int kAttnBKV = 128;
-constexpr int kAttnStages = 3;      // K and V rings
+constexpr int kAttnStages = 4;      // K and V rings
 constexpr uint32_t kAttnTile = 128 * 64 * 2;  // 16 KB
-// Q x2 + K,V rings + P (2 warpgroups x 2 sub-tiles) + alignment slack + barriers
-constexpr size_t kAttnSmem = size_t(kAttnTile) * (2 + 2 * kAttnStages + 4) + 1024 + 256 + 4096;  // + row-stat exchange (v4)
+// Q x2 + K,V rings + alignment slack + barriers (P lives in TMEM)
+constexpr size_t kAttnSmem = size_t(kAttnTile) * (2 + 2 * kAttnStages) + 1024 + 512;
 
 }  // namespace f5

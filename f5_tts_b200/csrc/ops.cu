@@ -59,6 +59,17 @@ int run_mask_rows(float* x, const uint8_t* filler, int BN, int rows, int C, cuda
   return check_launch("mask_rows_kernel");
 }
 
+int run_mask_rows_len(float* x, const int* valid_len, int B, int N, int rows, int C, cudaStream_t s) {
+  mask_rows_len_kernel<float><<<rows, 128, 0, s>>>(x, valid_len, B, N, rows, C);
+  count_launch();
+  return check_launch("mask_rows_len_kernel<float>");
+}
+int run_mask_rows_len_half(__half* x, const int* valid_len, int B, int N, int rows, int C, cudaStream_t s) {
+  mask_rows_len_kernel<__half><<<rows, 128, 0, s>>>(x, valid_len, B, N, rows, C);
+  count_launch();
+  return check_launch("mask_rows_len_kernel<half>");
+}
+
 int run_grn(__half* g, float* partial, float* nx, const float* gamma, const float* beta, int B, int N, int C,
             cudaStream_t s) {
   // `partial` must hold B * ceil(N / kGrnRows) * C floats

@@ -12,7 +12,6 @@ from __future__ import annotations
 import os
 import re
 import wave
-from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 import torch
@@ -251,10 +250,34 @@ def infer_process(ref_audio, ref_text, gen_text, model_obj, vocoder, mel_spec_ty
                                     device=device))
 
 
+def cross_fade_concat(waves: list, fade: int):
+    """utils_infer.py:549-585 on tensors that stay where they are (device or host): sequentially, the tail of the running
+    result and the head of the next chunk are blended over `fade` samples with linear ramps."""
+    final = waves[0]
+    for nxt in waves[1:]:
+        n = min(fade, final.shape[-1], nxt.shape[-1])
+        if n <= 0:
+            final = torch.cat([final, nxt])
+            continue
+        ramp = torch.linspace(0.0, 1.0, n, device=final.device, dtype=final.dtype)
+        mixed = final[-n:] * (1.0 - ramp) + nxt[:n] * ramp
+        final = torch.cat([final[:-n], mixed, nxt[n:]])
+    return final
+
+
+MAX_CHUNK_BATCH = 16  # text chunks per batched sampler call
+
+
 def infer_batch_process(ref_audio, ref_text, gen_text_batches, model_obj, vocoder, mel_spec_type="vocos", progress=None,
                         target_rms=0.1, cross_fade_duration=0.15, nfe_step=32, cfg_strength=2.0, sway_sampling_coef=-1,
                         speed=1, fix_duration=None, device=None, streaming=False, chunk_size=2048):
-    """utils_infer.py:440-593 — generator yielding (final_wave, sr, spectrogram) or streaming (chunk, sr)."""
+    """utils_infer.py:440-593 — generator yielding (final_wave, sr, spectrogram) or streaming (chunk, sr).
+
+    The reference samples every text chunk in its own B = 1 call from a thread pool (utils_infer.py:540-541) and
+    cross-fades the chunks on the host.  Here all chunks of a request go through ONE batched sampler call
+    (`exact_varlen=True`: each chunk is computed exactly as if it were alone, so the result equals the per-chunk loop),
+    sharing the prompt mel; the vocoder output, RMS gain and cross-fade stay on the device and the finished waveform
+    crosses to the host once."""
     if mel_spec_type != "vocos":
         raise NotImplementedError("bigvgan mel/vocoder is out of scope")
     audio, sr = ref_audio
@@ -270,52 +293,61 @@ def infer_batch_process(ref_audio, ref_text, gen_text_batches, model_obj, vocode
     audio = audio.to(device)
     if len(ref_text[-1].encode("utf-8")) == 1:
         ref_text = ref_text + " "
+    ref_audio_len = audio.shape[-1] // hop_length
 
-    def synth(gen_text):  # `_infer_basic`, utils_infer.py:477-520
+    def plan(gen_text):  # duration heuristic of `_infer_basic`, utils_infer.py:477-493
         local_speed = 0.3 if len(gen_text.encode("utf-8")) < 10 else speed
-        tokens = convert_char_to_pinyin([ref_text + gen_text])
-        ref_audio_len = audio.shape[-1] // hop_length
         if fix_duration is not None:
-            duration = int(fix_duration * target_sample_rate / hop_length)
-        else:
-            ref_text_len, gen_text_len = len(ref_text.encode("utf-8")), len(gen_text.encode("utf-8"))
-            duration = ref_audio_len + int(ref_audio_len / ref_text_len * gen_text_len / local_speed)
-        with torch.inference_mode():
-            generated, _ = model_obj.sample(cond=audio, text=tokens, duration=duration, steps=nfe_step,
-                                            cfg_strength=cfg_strength, sway_sampling_coef=sway_sampling_coef)
-            generated = generated.to(torch.float32)[:, ref_audio_len:, :].permute(0, 2, 1)
-            wave_out = vocoder.decode(generated)
-            if rms < target_rms:
-                wave_out = wave_out * rms / target_rms
-            return wave_out.squeeze().cpu().numpy(), generated
+            return int(fix_duration * target_sample_rate / hop_length)
+        ref_text_len, gen_text_len = len(ref_text.encode("utf-8")), len(gen_text.encode("utf-8"))
+        return ref_audio_len + int(ref_audio_len / ref_text_len * gen_text_len / local_speed)
 
+    def synth(gen_texts):
+        """[(wave tensor [n], generated mel tensor [100, frames])] for a group of chunks — one sampler call."""
+        tokens = convert_char_to_pinyin([ref_text + t for t in gen_texts])
+        durations = [plan(t) for t in gen_texts]
+        with torch.inference_mode():
+            if len(gen_texts) == 1:
+                generated, _ = model_obj.sample(cond=audio, text=tokens, duration=durations[0], steps=nfe_step,
+                                                cfg_strength=cfg_strength, sway_sampling_coef=sway_sampling_coef)
+                # the sampler may lengthen a chunk (cfm.py:134-137): the row count is its answer
+                durations = [generated.shape[1]]
+            else:
+                cond = model_obj.mel_spec(audio, frames_last=False)  # prompt mel, once: [1, n_ref, 100]
+                cond = cond.expand(len(gen_texts), -1, -1).contiguous()
+                dur = torch.tensor(durations, dtype=torch.long, device=cond.device)
+                lens = torch.full((len(gen_texts),), cond.shape[1], dtype=torch.long, device=cond.device)
+                n_text = [len(t) for t in tokens]
+                durations = [max(max(nt, cond.shape[1]) + 1, d) for nt, d in zip(n_text, durations)]  # cfm.py:134-137
+                generated, _ = model_obj.sample(cond=cond, text=tokens, duration=dur, lens=lens, steps=nfe_step,
+                                                cfg_strength=cfg_strength, sway_sampling_coef=sway_sampling_coef,
+                                                exact_varlen=True)
+            out = []
+            for i, d in enumerate(durations):
+                mel = generated[i: i + 1, ref_audio_len:d, :].to(torch.float32).permute(0, 2, 1)
+                wave_out = vocoder.decode(mel.contiguous())
+                if rms < target_rms:
+                    wave_out = wave_out * rms / target_rms
+                out.append((wave_out.squeeze(0), mel[0]))
+            return out
+
+    batches = list(gen_text_batches)
     if streaming:
-        it = progress.tqdm(gen_text_batches) if progress is not None else gen_text_batches
+        it = progress.tqdm(batches) if progress is not None else batches
         for gen_text in it:
-            wave_np, _ = synth(gen_text)
+            wave_np = synth([gen_text])[0][0].cpu().numpy()
             for j in range(0, len(wave_np), chunk_size):
                 yield wave_np[j: j + chunk_size], target_sample_rate
         return
 
-    waves, specs = [], []
-    with ThreadPoolExecutor() as pool:  # concurrent sample() calls are safe: per-thread workspaces (model.py)
-        futures = [pool.submit(synth, t) for t in gen_text_batches]
-        for fut in (progress.tqdm(futures) if progress is not None else futures):
-            wave_np, mel = fut.result()
-            waves.append(wave_np)
-            specs.append(mel[0].cpu().numpy())
-    if not waves:
+    groups = [batches[i: i + MAX_CHUNK_BATCH] for i in range(0, len(batches), MAX_CHUNK_BATCH)]
+    results = []
+    for grp in (progress.tqdm(groups) if progress is not None else groups):
+        results.extend(synth(grp))
+    if not results:
         yield None, target_sample_rate, None
         return
-    final = waves[0]
-    for nxt in waves[1:]:
-        if cross_fade_duration <= 0:
-            final = np.concatenate([final, nxt])
-            continue
-        n = min(int(cross_fade_duration * target_sample_rate), len(final), len(nxt))
-        if n <= 0:
-            final = np.concatenate([final, nxt])
-            continue
-        mixed = final[-n:] * np.linspace(1, 0, n) + nxt[:n] * np.linspace(0, 1, n)
-        final = np.concatenate([final[:-n], mixed, nxt[n:]])
-    yield final, target_sample_rate, np.concatenate(specs, axis=1)
+    fade = int(cross_fade_duration * target_sample_rate) if cross_fade_duration > 0 else 0
+    final = cross_fade_concat([w for w, _ in results], fade)
+    spec = torch.cat([m for _, m in results], dim=1)
+    yield final.cpu().numpy(), target_sample_rate, spec.cpu().numpy()

@@ -245,7 +245,8 @@ class _Backbone(nn.Module):
         with self._ws_lock:
             self._ws_free.setdefault((torch.device(device), int(stream)), []).append(ws)
 
-    def run(self, y, step_cond, text, t_grid, duration, cfg_strength, trajectory=None, v_out=None, use_graph=True):
+    def run(self, y, step_cond, text, t_grid, duration, cfg_strength, trajectory=None, v_out=None, use_graph=True,
+            exact_varlen=False):
         """One engine call = len(t_grid)-1 Euler steps.  All tensors on the CUDA device, fp32 / int64 / int32."""
         st = self.engine()
         L = _lib.lib()
@@ -266,6 +267,7 @@ class _Backbone(nn.Module):
         a.trajectory = trajectory.data_ptr() if trajectory is not None else None
         a.use_graph = 1 if use_graph else 0
         a.v_out = v_out.data_ptr() if v_out is not None else None
+        a.exact_varlen = 1 if (exact_varlen and duration is not None) else 0
         try:
             with torch.cuda.device(y.device):
                 _lib.check(L.f5_sample(st["handle"], C.byref(a), ws.data_ptr(), ws.numel(), stream), "f5_sample")
@@ -397,8 +399,11 @@ class CFM(nn.Module):
     @torch.no_grad()
     def sample(self, cond, text, duration, *, lens=None, steps=32, cfg_strength=1.0, sway_sampling_coef=None,
                seed: int | None = None, max_duration=65536, vocoder: Callable | None = None, use_epss=True,
-               no_ref_audio=False, duplicate_test=False, t_inter=0.1, edit_mask=None, y0: torch.Tensor | None = None):
-        """model/cfm.py:83-229.  Extra keyword `y0` injects the initial noise (parity tests)."""
+               no_ref_audio=False, duplicate_test=False, t_inter=0.1, edit_mask=None, y0: torch.Tensor | None = None,
+               exact_varlen: bool = False):
+        """model/cfm.py:83-229.  Extra keywords: `y0` injects the initial noise (parity tests, SURVEY.md §8c);
+        `exact_varlen=True` (batch > 1) computes every sample exactly as if it were alone in the batch with its own
+        duration — the result of a loop of single-sample calls, in one batched call (f5_sample_args.exact_varlen)."""
         self.eval()
         if cond.ndim == 2:  # raw wave -> mel [b, n, d]
             cond = self.mel_spec(cond, frames_last=False)
@@ -463,7 +468,8 @@ class CFM(nn.Module):
         y = y0.float().contiguous().clone()
         trajectory = torch.empty((steps + 1, batch, n_frames, self.num_channels), device=device, dtype=torch.float32)
         self.transformer.run(y, step_cond.float().contiguous(), text.to(torch.int64).contiguous(), t.tolist(), dur32,
-                             cfg_strength, trajectory=trajectory, use_graph=self.use_cuda_graph)
+                             cfg_strength, trajectory=trajectory, use_graph=self.use_cuda_graph,
+                             exact_varlen=exact_varlen)
         self.transformer.clear_cache()
 
         out = torch.where(cond_mask, cond, trajectory[-1].to(dtype))

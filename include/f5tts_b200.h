@@ -70,6 +70,25 @@ typedef struct {
   int inner, pe_heads;
   int weights_static;      /* 1 = W was NOT written by the kernel preceding this call on the stream (model weights):
                               its first tiles are fetched ahead of the programmatic-dependent-launch wait */
+  /* Fused A-operand normalisation (AdaLayerNorm / RMSNorm in front of a projection: model/modules.py:312-326,716,
+   * 753-754; unett.py:300-301).  norm_x != NULL: the kernel first computes A[r, :] = fp16(norm(norm_x[r, :])) into the
+   * caller's A buffer (which then is scratch, [rows, k] with lda == k) and multiplies by it — one kernel instead of
+   * f5_row_norm + f5_gemm.  Plain GEMM with batches == 1, k a multiple of 128 and <= 1024, epilogues QKV_ROPE or
+   * F16 + GELU_TANH.  mode 0: LN(eps) * (1 + a[c]) + b[c]; mode 2: x/||x|| * sqrt(k) * a[c]; a, b are indexed with
+   * step_ptr like gate (norm_step_stride elements per step).  norm_counters: ceil(rows / 128) ints, zeroed by the
+   * caller before the first launch; they count finished rows cumulatively, launch n (0-based, *step_ptr) expects
+   * rows x (n + 1). */
+  const float* norm_x;
+  int norm_mode;
+  const float* norm_a;
+  const float* norm_b;
+  long long norm_step_stride;
+  int* norm_counters;
+  float norm_eps;
+  /* Packed / variable-length execution: 1 = output tiles whose rows all lie past row_len of their sample are skipped
+   * entirely (not loaded, multiplied or stored: their output rows keep whatever the buffer held).  Needs row_len and
+   * seq.  The reference's counterpart is its masked mode (flash_attn_varlen / attn_mask, modules.py:513-540). */
+  int skip_padded_tiles;
 } f5_gemm_args;
 int f5_gemm(const void* A, const void* W, const f5_gemm_args* args, f5_stream_t stream);
 /* Tile shape f5_gemm would run `args` with (after bn = 0 resolution): *bn tile width, *cta_pair 0/1. */
@@ -166,6 +185,12 @@ typedef struct {
   int use_graph;             /* capture one NFE step into a CUDA graph and replay it */
   float* v_out;              /* optional device fp32 [Be, N, mel]: raw backbone output of the LAST step (the value
                                 transformer(x, cond, text, time, mask, cfg_infer=...) returns, dit.py:367-370) */
+  int exact_varlen;          /* with duration != NULL: 1 = every sample is computed exactly as if it were ALONE in the batch
+                                with N = duration[b] — text blocks, conv position embedding and attention see nothing past
+                                the sample's end, padded tiles are skipped.  This is what a loop of B = 1 sample() calls
+                                computes (the reference's per-chunk loop, infer/utils_infer.py:540-541), in one batch.
+                                0 = the reference's batched semantics (padded rows computed; attended unless
+                                arch.attn_mask_enabled) */
 } f5_sample_args;
 size_t f5_sample_workspace_bytes(const f5_engine* e, int B, int N, int steps, float cfg_strength);
 int f5_sample(f5_engine* e, const f5_sample_args* args, void* workspace, size_t ws_bytes, f5_stream_t stream);

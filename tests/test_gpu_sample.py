@@ -186,3 +186,37 @@ def test_errors_are_loud():
     model, _ = build(O.f5tts_base(), 1234)
     with pytest.raises(NotImplementedError):
         model(torch.zeros(1, 10, 100), torch.zeros(1, 10, dtype=torch.long))
+
+
+@pytest.mark.parametrize("arch", ["f5tts_base", "f5tts_v1_base"])
+def test_exact_varlen_batch_equals_single_calls(arch):
+    """exact_varlen (f5_sample_args): one batched call over samples of different lengths == a loop of B = 1 calls, which
+    is what the reference's infer_batch_process computes per text chunk (utils_infer.py:540-541).  Also against the CPU
+    oracle run sample by sample.  Covers the strict text-block masking, per-sample conv padding, key masking and the
+    skipping of padded tiles (lengths chosen to leave whole 128-row tiles of padding)."""
+    cfg = getattr(O, arch)()
+    model, sd = build(cfg, 1234)
+    g = torch.Generator().manual_seed(33)
+    n_ref, durs = 60, [420, 150, 297]
+    cond = torch.randn(1, n_ref, 100, generator=g)
+    text = torch.randint(0, 2545, (3, 50), generator=g)
+    text[1, 30:] = -1
+    y0 = [torch.randn(1, d, 100, generator=g) for d in durs]
+    kw = dict(steps=3, cfg_strength=2.0, sway_sampling_coef=-1.0)
+    singles = []
+    for b, d in enumerate(durs):
+        tb = text[b: b + 1, : int((text[b] != -1).sum())]
+        o, _ = model.sample(cond.to(DEV), tb.to(DEV), d, **kw, y0=y0[b].to(DEV))
+        singles.append(o)
+        if b == 1:  # one sample against the fp32 oracle as well
+            ref = O.sample(sd, cfg, cond, tb, d, **kw, y0=y0[b])
+            assert rel(o, ref.out) <= TOL
+    y0b = torch.zeros(3, max(durs), 100)
+    for b, d in enumerate(durs):
+        y0b[b, :d] = y0[b][0]
+    out, _ = model.sample(cond.expand(3, -1, -1).contiguous().to(DEV), text.to(DEV), torch.tensor(durs).to(DEV),
+                          lens=torch.full((3,), n_ref).to(DEV), **kw, y0=y0b.to(DEV), exact_varlen=True)
+    for b, d in enumerate(durs):
+        r = rel(out[b, :d], singles[b][0])
+        print(f"[exact_varlen {arch}] sample {b} ({d} frames): batched vs single rel-L2 {r:.3e}")
+        assert r <= 1e-3

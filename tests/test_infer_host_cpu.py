@@ -83,15 +83,21 @@ def test_load_wav_pcm16(tmp_path):
 
 
 class _FakeModel:
-    """Records the sampler calls of `_infer_basic` (utils_infer.py:477-520) and returns a ramp mel."""
+    """Records the sampler calls of `_infer_basic` (utils_infer.py:477-520) and returns a ramp mel.  A request with several
+    text chunks arrives as ONE batched call (prompt mel expanded over the batch, per-chunk durations, exact_varlen)."""
 
     def __init__(self):
         self.calls = []
 
-    def sample(self, cond, text, duration, steps, cfg_strength, sway_sampling_coef):
-        self.calls.append(dict(cond=cond.clone(), text=text, duration=duration, steps=steps, cfg=cfg_strength,
-                               sway=sway_sampling_coef))
-        mel = torch.arange(duration, dtype=torch.float32).view(1, duration, 1).repeat(1, 1, 100)
+    def mel_spec(self, audio, frames_last=False):  # [1, nw] -> [1, n, 100]; the value marks "computed from the prompt"
+        assert not frames_last
+        return audio[:, : (audio.shape[-1] // 256) * 256].reshape(1, -1, 256)[:, :, :100].contiguous()
+
+    def sample(self, cond, text, duration, steps, cfg_strength, sway_sampling_coef, lens=None, exact_varlen=False):
+        durs = [duration] if isinstance(duration, int) else [int(d) for d in duration]
+        self.calls.append(dict(cond=cond.clone(), text=text, duration=durs, steps=steps, cfg=cfg_strength,
+                               sway=sway_sampling_coef, lens=lens, exact=exact_varlen))
+        mel = torch.arange(max(durs), dtype=torch.float32).view(1, -1, 1).repeat(len(durs), 1, 100)
         return mel, None
 
 
@@ -112,15 +118,16 @@ def test_infer_batch_process_chunk_loop():
     wave_np, got_sr, spec = out[0]
     assert got_sr == sr
     ref_len = sr // infer.hop_length
-    assert len(model.calls) == 2
-    for c in model.calls:
-        assert c["steps"] == 7 and c["cfg"] == 1.5 and c["sway"] == -0.5
-        assert c["cond"].shape == (1, sr)                                  # mono mix
-        assert torch.allclose(c["cond"], torch.full((1, sr), 0.1), atol=1e-6)  # RMS-normalised to 0.1
+    assert len(model.calls) == 1                                           # both chunks in one batched sampler call
+    c = model.calls[0]
+    assert c["steps"] == 7 and c["cfg"] == 1.5 and c["sway"] == -0.5 and c["exact"] is True
+    assert c["cond"].shape == (2, ref_len, 100)                            # prompt mel of the mono mix, once per chunk
+    assert torch.allclose(c["cond"], torch.full((2, ref_len, 100), 0.1), atol=1e-6)  # RMS-normalised to 0.1
+    assert c["lens"].tolist() == [ref_len, ref_len] and len(c["text"]) == 2
     # duration heuristic: ref frames + ref frames / ref bytes * gen bytes / speed (utils_infer.py:487-493)
     rt = ref_text + " "
     durs = [ref_len + int(ref_len / len(rt.encode()) * len(b.encode()) / 1.0) for b in batches]
-    assert sorted(c["duration"] for c in model.calls) == sorted(durs)
+    assert c["duration"] == durs
     # per chunk: generated part only, vocoded, gain undone; then cross-faded
     lens = [256 * (d - ref_len - 1) for d in durs]
     fade = int(0.1 * sr)
@@ -139,7 +146,7 @@ def test_infer_batch_process_streaming_and_short_text():
     ref_len = sr // infer.hop_length
     # < 10 bytes of text -> local speed 0.3 (utils_infer.py:479-481)
     dur = ref_len + int(ref_len / len("ok then. ".encode()) * len("hi.".encode()) / 0.3)
-    assert model.calls[0]["duration"] == dur
+    assert model.calls[0]["duration"] == [dur] and model.calls[0]["cond"].shape == (1, sr)
     total = sum(len(c[0]) for c in chunks)
     assert total == 256 * (dur - ref_len - 1) and all(c[1] == sr for c in chunks)
     assert all(len(c[0]) <= 1000 for c in chunks)
