@@ -4,8 +4,81 @@
 #include "internal.h"
 
 #include <cstdlib>
+#include <map>
+#include <mutex>
+#include <utility>
+#include <vector>
 
 namespace f5 {
+
+// ---- per-device constant tables of the FFT kernels (twiddles, Hann window) and per-filterbank band indices ----------
+namespace {
+std::mutex g_fft_mu;
+std::map<int, FftTables> g_fft_tables;                                  // device ordinal -> tables
+std::map<std::pair<int, const void*>, std::pair<short*, short*>> g_bands;  // (device, fb pointer) -> (lo, hi) [n_mels]
+}  // namespace
+
+static int fft_tables(FftTables* out, cudaStream_t s) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lk(g_fft_mu);
+  auto it = g_fft_tables.find(dev);
+  if (it == g_fft_tables.end()) {
+    float2* tw = nullptr;
+    float* hann = nullptr;
+    if (int rc = check_cuda(cudaMalloc(&tw, sizeof(float2) * kNfft / 2), "fft tables")) return rc;
+    if (int rc = check_cuda(cudaMalloc(&hann, sizeof(float) * kNfft), "fft tables")) return rc;
+    fft_tables_kernel<<<kNfft / 256, 256, 0, s>>>(tw, hann);  // same stream as the first user: ordered before it
+    if (int rc = check_launch("fft_tables_kernel")) return rc;
+    // later users may sit on other streams: the tables must be complete before this call returns
+    if (int rc = check_cuda(cudaStreamSynchronize(s), "fft tables sync")) return rc;
+    it = g_fft_tables.emplace(dev, FftTables{tw, hann}).first;
+  }
+  *out = it->second;
+  return 0;
+}
+
+// First / last non-zero bin of every mel filter of the caller's dense [513, n_mels] filterbank (one D2H read per
+// filterbank tensor; the Python side keeps one per device).
+static int mel_bands(const float* fb, int n_mels, const short** lo, const short** hi, cudaStream_t s) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lk(g_fft_mu);
+  const auto key = std::make_pair(dev, static_cast<const void*>(fb));
+  auto it = g_bands.find(key);
+  if (it == g_bands.end()) {
+    std::vector<float> h((size_t)kBins * n_mels);
+    if (int rc = check_cuda(cudaMemcpyAsync(h.data(), fb, sizeof(float) * h.size(), cudaMemcpyDeviceToHost, s), "fb d2h")) return rc;
+    if (int rc = check_cuda(cudaStreamSynchronize(s), "fb sync")) return rc;
+    std::vector<short> l(n_mels, 1), u(n_mels, 0);  // empty band: lo > hi
+    for (int m = 0; m < n_mels; ++m) {
+      int first = -1, last = -1;
+      for (int f = 0; f < kBins; ++f)
+        if (h[(size_t)f * n_mels + m] != 0.0f) {
+          if (first < 0) first = f;
+          last = f;
+        }
+      if (first >= 0) l[m] = (short)first, u[m] = (short)last;
+    }
+    short *dl = nullptr, *du = nullptr;
+    if (int rc = check_cuda(cudaMalloc(&dl, sizeof(short) * n_mels), "band index")) return rc;
+    if (int rc = check_cuda(cudaMalloc(&du, sizeof(short) * n_mels), "band index")) return rc;
+    cudaMemcpyAsync(dl, l.data(), sizeof(short) * n_mels, cudaMemcpyHostToDevice, s);
+    cudaMemcpyAsync(du, u.data(), sizeof(short) * n_mels, cudaMemcpyHostToDevice, s);
+    if (int rc = check_cuda(cudaStreamSynchronize(s), "band index sync")) return rc;
+    if (g_bands.size() >= 64) {  // filterbanks are per-process constants; a churning caller must not leak without bound
+      for (auto& kv : g_bands) {
+        cudaFree(kv.second.first);
+        cudaFree(kv.second.second);
+      }
+      g_bands.clear();
+    }
+    it = g_bands.emplace(key, std::make_pair(dl, du)).first;
+  }
+  *lo = it->second.first;
+  *hi = it->second.second;
+  return 0;
+}
 
 static inline int grid_for(long long n, int block, int cap = 148 * 16) {
   long long g = (n + block - 1) / block;
@@ -167,7 +240,12 @@ int f5_mel_spectrogram(const float* wav, int B, int nw, const float* fb, int n_m
     return -1;
   }
   const int T = 1 + nw / kHop;
-  mel_stft_kernel<<<dim3(T, B), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(wav, nw, T, fb, n_mels, out, out_btc);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  FftTables tab;
+  if (int rc = fft_tables(&tab, s)) return rc;
+  const short *lo = nullptr, *hi = nullptr;
+  if (int rc = mel_bands(fb, n_mels, &lo, &hi, s)) return rc;
+  mel_stft_kernel<<<dim3(T, B), 256, 0, s>>>(wav, nw, T, fb, n_mels, lo, hi, tab, out, out_btc);
   count_launch();
   return check_launch("mel_stft_kernel");
 }
@@ -256,9 +334,11 @@ int f5_vocos_decode(const f5_vocos_weights* w, const float* mel, int B, int T, v
   gh.rows = R; gh.batches = 1; gh.n_out = 1026; gh.k = 512; gh.lda = 512; gh.ldw = 512; gh.bn = 128;
   gh.epi = F5_EPI_F32; gh.act = F5_ACT_NONE; gh.bias = w->head_b; gh.out = head; gh.ldo = 1026;
   if ((rc = f5_gemm(a, w->head_w, &gh, stream))) return rc;
-  istft_frames_kernel<<<R, 256, 0, s>>>(head, 1026, frames);
+  FftTables tab;
+  if ((rc = fft_tables(&tab, s))) return rc;
+  istft_frames_kernel<<<R, 256, 0, s>>>(head, 1026, frames, tab);
   const long long total = (long long)B * kHop * (T - 1);
-  istft_ola_kernel<<<grid_for(total, 256), 256, 0, s>>>(frames, T, wav, B);
+  istft_ola_kernel<<<grid_for(total, 256), 256, 0, s>>>(frames, T, wav, B, tab);
   count_launch(2);
   return check_launch("vocos istft kernels");
 }

@@ -105,6 +105,9 @@ def convert_char_to_pinyin(text_list, polyphone=True):
     try:
         import rjieba
         from pypinyin import Style, lazy_pinyin
+
+        if not callable(getattr(rjieba, "cut", None)):  # an empty stand-in module is not the package
+            rjieba = None
     except Exception:  # noqa: BLE001
         rjieba = None
 
@@ -192,8 +195,10 @@ def load_checkpoint(model, ckpt_path, device: str, dtype=None, use_ema=True):
 
 
 def load_model(model_cls, model_cfg, ckpt_path, mel_spec_type=mel_spec_type, vocab_file="", ode_method=ode_method,
-               use_ema=True, device=device):
-    """utils_infer.py:238-276"""
+               use_ema=True, device=device, packed_cache_dir=None):
+    """utils_infer.py:238-276.  `packed_cache_dir` (extra, default off): keep the kernel-layout operands of this
+    checkpoint (fp16 K-major weights, stacked QKV / AdaLN matrices, re-tiled conv weights; weights.py) in that folder and
+    read them straight onto the GPU on later loads instead of re-packing 0.67 GB through conversion kernels."""
     if vocab_file == "":
         raise FileNotFoundError("vocab_file is required (the reference defaults to its packaged "
                                 "infer/examples/vocab.txt, utils_infer.py:248-249; that data file is not vendored here)")
@@ -207,6 +212,13 @@ def load_model(model_cls, model_cfg, ckpt_path, mel_spec_type=mel_spec_type, voc
     ).to(device)
     if ckpt_path:
         model = load_checkpoint(model, ckpt_path, device, dtype=None, use_ema=use_ema)
+        if packed_cache_dir and "cuda" in str(device):
+            from . import weights as _w
+
+            os.makedirs(packed_cache_dir, exist_ok=True)
+            path = os.path.join(packed_cache_dir, f"f5pack_{_w.cache_key(ckpt_path, model.transformer)}.safetensors")
+            if not (os.path.exists(path) and _w.attach_packed(model.transformer, path, device)):
+                _w.save_packed(model.transformer, path)
     return model
 
 

@@ -68,7 +68,7 @@ def assets(tmp_path_factory, golden_dir):
     torch.save(full, str(vdir / "pytorch_model.bin"))
     tts = api.F5TTS(model="F5TTS_Base", ckpt_file=ckpt, vocab_file=os.path.join(golden_dir, "vocab.txt"),
                     vocoder_local_path=str(vdir), device=DEV)
-    return dict(tts=tts, sd=sd, vsd=vsd, cfg=cfg, ref=os.path.join(golden_dir, "basic_ref_en.wav"))
+    return dict(tts=tts, sd=sd, vsd=vsd, cfg=cfg, ckpt=ckpt, ref=os.path.join(golden_dir, "basic_ref_en.wav"))
 
 
 def expected_chunk(a, gen_text, y0):
@@ -132,3 +132,41 @@ def test_f5tts_infer_multi_chunk_shapes_and_files(assets, tmp_path):
     back, sr2 = infer._load_wav(fw)
     assert sr2 == 24000 and back.shape[-1] == len(wav)
     assert np.load(fs).shape == spec.shape
+
+
+def test_packed_weight_cache_roundtrip(assets, tmp_path, golden_dir):
+    """the kernel-layout operands are cached on disk next to the checkpoint identity; the second load
+    reads them straight onto the GPU (no re-packing) and samples bit-identically."""
+    import glob
+
+    from f5_tts_b200 import weights as Wt
+
+    a = assets
+    ckpt = a["ckpt"]
+    cls, arch = api.MODEL_ARCH["F5TTS_Base"]
+    vocab = os.path.join(golden_dir, "vocab.txt")
+    cache = str(tmp_path / "pack")
+    m1 = infer.load_model(cls, arch, ckpt, vocab_file=vocab, device=DEV, packed_cache_dir=cache)
+    files = glob.glob(os.path.join(cache, "f5pack_*.safetensors"))
+    assert len(files) == 1 and os.path.getsize(files[0]) > 600e6  # 0.67 GB of fp16 operands + fp32 table / biases
+    calls = {"n": 0}
+    orig = Wt.packed_tensors
+
+    def counting(m):
+        calls["n"] += 1
+        return orig(m)
+
+    Wt.packed_tensors = counting
+    try:
+        m2 = infer.load_model(cls, arch, ckpt, vocab_file=vocab, device=DEV, packed_cache_dir=cache)
+        g = torch.Generator().manual_seed(3)
+        cond = torch.randn(1, 40, 100, generator=g).to(DEV)
+        text = torch.randint(0, 2545, (1, 30), generator=g).to(DEV)
+        y0 = torch.randn(1, 150, 100, generator=g).to(DEV)
+        kw = dict(steps=2, cfg_strength=2.0, sway_sampling_coef=-1.0)
+        o2, _ = m2.sample(cond.half(), text, 150, **kw, y0=y0)
+        assert calls["n"] == 0, "the second load must not re-pack"
+    finally:
+        Wt.packed_tensors = orig
+    o1, _ = m1.sample(cond.half(), text, 150, **kw, y0=y0)
+    assert torch.equal(o1, o2)
