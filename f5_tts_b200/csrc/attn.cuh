@@ -93,8 +93,8 @@ __device__ __forceinline__ void ex2_poly2(uint64_t x2, float& e0, float& e1) {
   float p0, p1, t0, t1;
   f2_unpack(p, p0, p1);
   f2_unpack(t, t0, t1);
-  e0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
-  e1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
+  e0 = __uint_as_float(__float_as_uint(p0) + (__float_as_uint(t0) << 23));  // exponent += n (two's complement wraps)
+  e1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(t1) << 23));
 }
 
 constexpr int kPolyOf8 = 3;  // element pairs (of every 8) whose 2^x runs on the FMA pipe instead of MUFU

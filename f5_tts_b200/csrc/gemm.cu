@@ -119,11 +119,13 @@ static int configure_inst() {
   X(192, 4, EPI_QKV_ROPE, ACT_NONE, false) \
   X(256, 3, EPI_QKV_ROPE, ACT_NONE, false) \
   X(256, 5, EPI_QKV_ROPE, ACT_NONE, true)  \
+  X(192, 6, EPI_QKV_ROPE, ACT_NONE, true)  \
   X(128, 6, EPI_QKV_ROPE, ACT_NONE, true)  \
   X(128, 5, EPI_F16, ACT_GELU_TANH, false) \
   X(192, 4, EPI_F16, ACT_GELU_TANH, false) \
   X(256, 3, EPI_F16, ACT_GELU_TANH, false) \
   X(256, 5, EPI_F16, ACT_GELU_TANH, true)  \
+  X(192, 6, EPI_F16, ACT_GELU_TANH, true)  \
   X(128, 6, EPI_F16, ACT_GELU_TANH, true)
 
 // cudaFuncSetAttribute is per device: the configured flag and the SM count are tracked per device ordinal, so one
@@ -174,6 +176,10 @@ int configure_kernels() {
   if (int rc = configure_inst<256, 5, EPI_F16, ACT_GELU_TANH, false, true>()) return rc;
   if (int rc = configure_inst<256, 5, EPI_RESID, ACT_NONE, false, true>()) return rc;
   if (int rc = configure_inst<256, 5, EPI_QKV_ROPE, ACT_NONE, false, true>()) return rc;
+  if (int rc = configure_inst<192, 6, EPI_F16, ACT_NONE, false, true>()) return rc;
+  if (int rc = configure_inst<192, 6, EPI_F16, ACT_GELU_TANH, false, true>()) return rc;
+  if (int rc = configure_inst<192, 6, EPI_RESID, ACT_NONE, false, true>()) return rc;
+  if (int rc = configure_inst<192, 6, EPI_QKV_ROPE, ACT_NONE, false, true>()) return rc;
   if (int rc = configure_inst<128, 6, EPI_F16, ACT_NONE, false, true>()) return rc;
   if (int rc = configure_inst<128, 6, EPI_F16, ACT_GELU_TANH, false, true>()) return rc;
   if (int rc = configure_inst<128, 6, EPI_RESID, ACT_NONE, false, true>()) return rc;
@@ -238,6 +244,10 @@ int gemm_run(const GemmPlan& pl, cudaStream_t s) {
   F5_GEMM_PAIR_CASE(256, 5, EPI_F16, ACT_GELU_TANH)
   F5_GEMM_PAIR_CASE(256, 5, EPI_RESID, ACT_NONE)
   F5_GEMM_PAIR_CASE(256, 5, EPI_QKV_ROPE, ACT_NONE)
+  F5_GEMM_PAIR_CASE(192, 6, EPI_F16, ACT_NONE)
+  F5_GEMM_PAIR_CASE(192, 6, EPI_F16, ACT_GELU_TANH)
+  F5_GEMM_PAIR_CASE(192, 6, EPI_RESID, ACT_NONE)
+  F5_GEMM_PAIR_CASE(192, 6, EPI_QKV_ROPE, ACT_NONE)
   F5_GEMM_PAIR_CASE(128, 6, EPI_F16, ACT_NONE)
   F5_GEMM_PAIR_CASE(128, 6, EPI_F16, ACT_GELU_TANH)
   F5_GEMM_PAIR_CASE(128, 6, EPI_RESID, ACT_NONE)
@@ -275,17 +285,18 @@ TileChoice pick_tile(long long rows, int batches, int n_out, int k, int epi, int
   const bool wide_ok = (epi == F5_EPI_F16 && (plain || gelu)) || ((epi == F5_EPI_RESID || epi == F5_EPI_QKV_ROPE) && plain);
   TileChoice best{128, 0};
   double best_cost = 1e30;
-  const int cand[5][2] = {{128, 0}, {192, 0}, {256, 0}, {128, 1}, {256, 1}};
+  const int cand[5][2] = {{128, 0}, {192, 0}, {256, 0}, {128, 1}, {256, 1}};  // {192, 1}: instantiated, on request only
   for (const auto& c : cand) {
     const int bn = c[0], pair = c[1];
     if ((pair || bn == 192) && !wide_ok) continue;
     if (bn > 128 && n_out < bn) continue;
     if (pair && n_out < 256) continue;
+    if (pair && bn == 192 && act == F5_ACT_GELU_ERF) continue;
     const long long tm = pair ? (rows + 255) / 256 : (rows + 127) / 128;
     const long long tiles = tm * ((n_out + bn - 1) / bn) * batches;
     const long long units = pair ? sms / 2 : sms;
     const double rounds = double((tiles + units - 1) / units);
-    const double main_clk = kb * (pair ? (bn == 256 ? 640.0 : 474.0) : 256.0 + 2.0 * bn);
+    const double main_clk = kb * (pair ? (bn == 256 ? 640.0 : bn == 192 ? 557.0 : 474.0) : 256.0 + 2.0 * bn);
     const double epi_clk = epi_col * bn;               // exposed (last tile): latency-bound, one warp per scheduler
     const double epi_pace = epi_clk * (50.0 / 60.0);  // overlapped with the next main loop it runs a little faster
     const double cost = (rounds - 1.0) * (main_clk > epi_pace ? main_clk : epi_pace) + main_clk + epi_clk + (pair ? 1500.0 /*cluster sync, remote barrier hops*/ : 0.0);
@@ -324,7 +335,7 @@ int gemm_plan(GemmPlan* pl, const void* A, const void* W, const f5_gemm_args* a)
   pl->epi = a->epi;
   pl->act = a->act;
   pl->conv = conv ? 1 : 0;
-  pl->pair = (!conv && want_pair && a->epi != F5_EPI_F32 && (bn == 128 || bn == 256)) ? 1 : 0;
+  pl->pair = (!conv && want_pair && a->epi != F5_EPI_F32 && bn >= 128) ? 1 : 0;
   pl->norma = a->norm_x != nullptr ? 1 : 0;
   if (pl->norma) {
     const bool epi_ok = (a->epi == F5_EPI_QKV_ROPE && a->act == F5_ACT_NONE) || (a->epi == F5_EPI_F16 && a->act == F5_ACT_GELU_TANH);
@@ -466,7 +477,7 @@ int f5_gemm_tile(const f5_gemm_args* args, int* bn, int* cta_pair) {
     pr = tc.pair;
   }
   *bn = b;
-  *cta_pair = (args->conv_taps == 0 && pr && args->epi != F5_EPI_F32 && (b == 128 || b == 256)) ? 1 : 0;
+  *cta_pair = (args->conv_taps == 0 && pr && args->epi != F5_EPI_F32 && b >= 128) ? 1 : 0;
   return 0;
 }
 

@@ -317,7 +317,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   constexpr uint32_t B_BYTES = BNL * kBK * 2;
   constexpr uint32_t TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;  // double-buffered accumulator
   static_assert(BN == 64 || BN == 128 || BN == 192 || BN == 256, "BN");
-  static_assert(!(PAIR && BN == 192), "pair tiles are 128 or 256 wide");
+  static_assert(!(PAIR && BN == 64), "pair tiles are 128, 192 or 256 wide");
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;

@@ -50,7 +50,8 @@ def test_gemm_f32(M, N, K, bn):
 
 
 @pytest.mark.parametrize("M,N,K,bn", [(256, 256, 64, 256), (1876, 2048, 1024, 256), (1876, 3072, 1024, 128), (700, 1024, 2048, 128),
-                                      (129, 512, 192, 256), (30000 // 8, 2048, 1024, 256)])
+                                      (129, 512, 192, 256), (30000 // 8, 2048, 1024, 256), (1876, 3072, 1024, 192),
+                                      (500, 1024, 2048, 192)])
 def test_gemm_cta_pair(M, N, K, bn):
     """cta_group::2 tiles (256 x bn per CTA pair): fp16+GELU, fp32 residual reduce-add and QKV+RoPE epilogues."""
     a, w = gen((M, K), 31), gen((N, K), 32, 1 / math.sqrt(K))

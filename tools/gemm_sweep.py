@@ -39,7 +39,7 @@ for M in Ms:
         nw = -(-200_000_000 // (N * K * 2))  # distinct weights > L2 (126 MB), as in the real step
         nw = nw if M < 8000 else max(6, nw // 4)
         row = []
-        for bn, pair in ((128, 0), (192, 0), (256, 0), (128, 1), (256, 1)):
+        for bn, pair in ((128, 0), (192, 0), (256, 0), (128, 1), (192, 1), (256, 1)):
             us, tf = bench(M, N, K, epi, act, bn, nw=nw, pair=pair)
             row.append(f"{'P' if pair else 'bn'}{bn}: {us:6.1f}us {tf:5.0f}TF")
         print(f"M={M:6d} {tag:7s} N={N:5d} K={K:5d} | " + " | ".join(row) + f" | auto={ops.gemm_tile(M, N, K, epi, act)}",

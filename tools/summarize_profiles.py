@@ -85,19 +85,37 @@ def metrics(rep, out, traffic_key=None):
             for k in KEYS:
                 if k in idx:
                     f.write(f"   {k} [{units[idx[k]]}] = {r[idx[k]]}\n")
+            def tobytes(k):
+                v, u = float(r[idx[k]].replace(",", "")), units[idx[k]]
+                return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
+
+            try:  # derived: achieved DRAM / L2 bandwidth of this launch (the HBM peak is MEASURED_PEAKS.json hbm_gbs)
+                dur, du = float(r[idx["gpu__time_duration.sum"]].replace(",", "")), units[idx["gpu__time_duration.sum"]]
+                dur_s = dur * {"ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1.0}.get(du, 1e-9)
+                dram = tobytes("dram__bytes_read.sum") + tobytes("dram__bytes_write.sum")
+                f.write(f"   derived: dram bytes {dram:.0f}  -> {dram / dur_s / 1e9:.1f} GB/s DRAM"
+                        f"  | L2 traffic {tobytes('lts__t_bytes.sum') / dur_s / 1e9:.1f} GB/s\n")
+            except Exception:  # noqa: BLE001
+                pass
             if traffic_key and traffic_key in r[idx["Kernel Name"]] and traffic is None:
-                def tobytes(k):
-                    v, u = float(r[idx[k]].replace(",", "")), units[idx[k]]
-                    return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
                 traffic = tobytes("dram__bytes_read.sum") + tobytes("dram__bytes_write.sum")
     print(open(os.path.join(PR, out)).read()[:3000])
     return traffic
 
 
 launches()
-t = metrics("prof_gemm.ncu-rep", f"{tag}_gemm_metrics.txt", traffic_key="0, 1, 0")  # EPI_F16 + GELU_TANH instantiation = FF1
-metrics("prof_attn.ncu-rep", f"{tag}_attn_metrics.txt")
+KEYS += ["sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+         "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
+         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"]
+traffic = {}
+t = metrics("prof_gemm.ncu-rep", f"{tag}_gemm_metrics.txt", traffic_key="gemm_tcgen05")
 if t is not None:
-    json.dump({"gemm_ff1_dram_bytes_per_launch": t, "source": f"profiles/{tag}_gemm_metrics.txt"},
-              open(os.path.join(PR, "traffic.json"), "w"))
-    print("traffic", t)
+    traffic["gemm_dram_bytes_per_launch"] = t
+t = metrics("prof_attn.ncu-rep", f"{tag}_attn_metrics.txt", traffic_key="attn_fwd")
+if t is not None:
+    traffic["attention_dram_bytes_per_launch"] = t
+metrics("prof_bw.ncu-rep", f"{tag}_bandwidth_kernels_metrics.txt")
+if traffic:
+    traffic["source"] = f"profiles/{tag}_gemm_metrics.txt / {tag}_attn_metrics.txt (first captured launch of each kernel)"
+    json.dump(traffic, open(os.path.join(PR, "traffic.json"), "w"))
+    print("traffic", traffic)
