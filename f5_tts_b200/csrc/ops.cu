@@ -5,6 +5,7 @@
 
 #include <cstdlib>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <utility>
 #include <vector>
@@ -265,21 +266,14 @@ size_t f5_vocos_workspace_bytes(int B, int T) {
   return n + 1024;
 }
 
-int f5_vocos_decode(const f5_vocos_weights* w, const float* mel, int B, int T, void* workspace, size_t ws_bytes,
-                    float* wav, f5_stream_t stream) {
-  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (w->dim != 512 || w->inter != 1536 || w->n_mels != 100 || w->layers > 8) {
-    set_error("vocos_decode: only the charactr/vocos-mel-24khz shape (512/1536, 100 mels, <= 8 layers) is built");
-    return -1;
-  }
-  if (B <= 0 || T < 2) {
-    set_error("vocos_decode: need B > 0 and at least 2 frames");
-    return -1;
-  }
-  if (ws_bytes < f5_vocos_workspace_bytes(B, T)) {
-    set_error("vocos_decode: workspace too small");
-    return -1;
-  }
+}  // extern "C"
+
+namespace {
+
+// All kernels of one decode, enqueued on `s` (graph capture or direct).
+int vocos_enqueue(const f5_vocos_weights* w, const float* mel, int B, int T, void* workspace, float* wav, FftTables tab,
+                  cudaStream_t s) {
+  f5_stream_t stream = reinterpret_cast<f5_stream_t>(s);
   const int R = B * T;
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
   auto take = [&](size_t bytes) {
@@ -334,13 +328,124 @@ int f5_vocos_decode(const f5_vocos_weights* w, const float* mel, int B, int T, v
   gh.rows = R; gh.batches = 1; gh.n_out = 1026; gh.k = 512; gh.lda = 512; gh.ldw = 512; gh.bn = 128;
   gh.epi = F5_EPI_F32; gh.act = F5_ACT_NONE; gh.bias = w->head_b; gh.out = head; gh.ldo = 1026;
   if ((rc = f5_gemm(a, w->head_w, &gh, stream))) return rc;
-  FftTables tab;
-  if ((rc = fft_tables(&tab, s))) return rc;
   istft_frames_kernel<<<R, 256, 0, s>>>(head, 1026, frames, tab);
   const long long total = (long long)B * kHop * (T - 1);
   istft_ola_kernel<<<grid_for(total, 256), 256, 0, s>>>(frames, T, wav, B, tab);
   count_launch(2);
   return check_launch("vocos istft kernels");
+}
+
+// One captured decode per (weights, workspace, B, T).  Only two kernels touch caller tensors — the im2col reads `mel`, the
+// overlap-add writes `wav` — and their node parameters are patched before every launch, so fresh input / output
+// allocations do not invalidate the graph.
+struct VocosGraph {
+  const void* w0;
+  const void* ws;
+  int B, T;
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  cudaGraphNode_t n_in = nullptr, n_out = nullptr;
+  int nodes = 0;
+  ~VocosGraph() {
+    if (exec) cudaGraphExecDestroy(exec);
+    if (graph) cudaGraphDestroy(graph);
+  }
+};
+std::mutex g_vocos_mu;
+std::vector<std::shared_ptr<VocosGraph>> g_vocos_graphs;
+
+}  // namespace
+
+extern "C" {
+
+int f5_vocos_decode(const f5_vocos_weights* w, const float* mel, int B, int T, void* workspace, size_t ws_bytes,
+                    float* wav, f5_stream_t stream) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (w->dim != 512 || w->inter != 1536 || w->n_mels != 100 || w->layers > 8) {
+    set_error("vocos_decode: only the charactr/vocos-mel-24khz shape (512/1536, 100 mels, <= 8 layers) is built");
+    return -1;
+  }
+  if (B <= 0 || T < 2) {
+    set_error("vocos_decode: need B > 0 and at least 2 frames");
+    return -1;
+  }
+  if (ws_bytes < f5_vocos_workspace_bytes(B, T)) {
+    set_error("vocos_decode: workspace too small");
+    return -1;
+  }
+  int rc;
+  if ((rc = configure_kernels())) return rc;
+  FftTables tab;
+  if ((rc = fft_tables(&tab, s))) return rc;
+  std::shared_ptr<VocosGraph> g;
+  {
+    std::lock_guard<std::mutex> lk(g_vocos_mu);
+    for (auto& e : g_vocos_graphs)
+      if (e->w0 == w->embed_w && e->ws == workspace && e->B == B && e->T == T) g = e;
+  }
+  if (!g) {
+    cudaStream_t cs;
+    if ((rc = check_cuda(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking), "capture stream"))) return rc;
+    if ((rc = check_cuda(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal), "begin capture"))) {
+      cudaStreamDestroy(cs);
+      return rc;
+    }
+    const unsigned long long before = f5_launch_count();
+    rc = vocos_enqueue(w, mel, B, T, workspace, wav, tab, cs);
+    g = std::make_shared<VocosGraph>();
+    const cudaError_t ce = cudaStreamEndCapture(cs, &g->graph);
+    cudaStreamDestroy(cs);
+    g->nodes = (int)(f5_launch_count() - before);
+    count_launch(-g->nodes);  // captured, not launched
+    if (rc) return rc;
+    if ((rc = check_cuda(ce, "end capture"))) return rc;
+    size_t nn = 0;
+    cudaGraphGetNodes(g->graph, nullptr, &nn);
+    std::vector<cudaGraphNode_t> nodes(nn);
+    cudaGraphGetNodes(g->graph, nodes.data(), &nn);
+    for (auto nd : nodes) {
+      cudaGraphNodeType ty;
+      if (cudaGraphNodeGetType(nd, &ty) != cudaSuccess || ty != cudaGraphNodeTypeKernel) continue;
+      cudaKernelNodeParams kp{};
+      if (cudaGraphKernelNodeGetParams(nd, &kp) != cudaSuccess) continue;
+      if (kp.func == reinterpret_cast<void*>(vocos_im2col_kernel)) g->n_in = nd;
+      if (kp.func == reinterpret_cast<void*>(istft_ola_kernel)) g->n_out = nd;
+    }
+    if (!g->n_in || !g->n_out) {
+      set_error("vocos_decode: could not locate the I/O kernel nodes of the captured graph");
+      return -7;
+    }
+    if ((rc = check_cuda(cudaGraphInstantiate(&g->exec, g->graph, 0), "graph instantiate"))) return rc;
+    g->w0 = w->embed_w;
+    g->ws = workspace;
+    g->B = B;
+    g->T = T;
+    std::lock_guard<std::mutex> lk(g_vocos_mu);
+    if (g_vocos_graphs.size() >= 32) g_vocos_graphs.erase(g_vocos_graphs.begin());
+    g_vocos_graphs.push_back(g);
+  }
+  // patch the two nodes that see caller tensors (same grid / block / other arguments as captured)
+  {
+    cudaKernelNodeParams kp{};
+    if ((rc = check_cuda(cudaGraphKernelNodeGetParams(g->n_in, &kp), "node params"))) return rc;
+    const float* mel_arg = mel;
+    void** args = kp.kernelParams;
+    void* patched[6] = {(void*)&mel_arg, args[1], args[2], args[3], args[4], args[5]};
+    kp.kernelParams = patched;
+    if ((rc = check_cuda(cudaGraphExecKernelNodeSetParams(g->exec, g->n_in, &kp), "patch im2col node"))) return rc;
+  }
+  {
+    cudaKernelNodeParams kp{};
+    if ((rc = check_cuda(cudaGraphKernelNodeGetParams(g->n_out, &kp), "node params"))) return rc;
+    float* wav_arg = wav;
+    void** args = kp.kernelParams;
+    void* patched[5] = {args[0], args[1], (void*)&wav_arg, args[3], args[4]};
+    kp.kernelParams = patched;
+    if ((rc = check_cuda(cudaGraphExecKernelNodeSetParams(g->exec, g->n_out, &kp), "patch overlap-add node"))) return rc;
+  }
+  if ((rc = check_cuda(cudaGraphLaunch(g->exec, s), "vocos graph launch"))) return rc;
+  count_launch(g->nodes);
+  return 0;
 }
 
 }  // extern "C"
