@@ -26,3 +26,20 @@ timeout 900 python bench.py --steps 5 --warmup 3 2> gpurun_out/bench.err | tee g
 tail -5 gpurun_out/bench.err
 echo "=== gemm sweep (M = 1876)"
 SWEEP_M=1876 timeout 600 python tools/gemm_sweep.py 2>&1 | tail -8 | tee gpurun_out/gemm_sweep.log
+echo "=== ncu launch list"
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 150 -c 400 --csv --log-file gpurun_out/launches.csv \
+  python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-extras > gpurun_out/ncu_launch_run.log 2>&1
+tail -1 gpurun_out/ncu_launch_run.log | cut -c1-200
+echo "=== ncu full: gemm (one block's four GEMMs)"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_tcgen05 -s 60 -c 5 -o gpurun_out/prof_gemm -f \
+  python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-extras > gpurun_out/ncu_gemm_run.log 2>&1
+tail -2 gpurun_out/ncu_gemm_run.log | cut -c1-200
+echo "=== ncu full: attention"
+timeout 900 ncu --set full --clock-control none --import-source on -k "regex:attn_fwd" -s 12 -c 2 -o gpurun_out/prof_attn -f \
+  python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-extras > gpurun_out/ncu_attn_run.log 2>&1
+tail -2 gpurun_out/ncu_attn_run.log | cut -c1-200
+echo "=== ncu full: bandwidth kernels (mel STFT, ISTFT, dwconv+LN, GRN, CFG+Euler, row norm)"
+timeout 900 ncu --set full --clock-control none -k "regex:mel_stft|istft_frames|istft_ola|dwconv7_ln|grn_sumsq|grn_apply|cfg_euler|row_norm" -c 14 -o gpurun_out/prof_bw -f \
+  python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-extras > gpurun_out/ncu_bw_run.log 2>&1
+tail -2 gpurun_out/ncu_bw_run.log | cut -c1-200
+ls -la gpurun_out | tail -30
