@@ -39,7 +39,7 @@ timeout 900 ncu --set full --clock-control none --import-source on -k "regex:att
   python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-extras > gpurun_out/ncu_attn_run.log 2>&1
 tail -2 gpurun_out/ncu_attn_run.log | cut -c1-200
 echo "=== ncu full: bandwidth kernels (mel STFT, ISTFT, dwconv+LN, GRN, CFG+Euler, row norm)"
-timeout 900 ncu --set full --clock-control none -k "regex:mel_stft|istft_frames|istft_ola|dwconv7_ln|grn_sumsq|grn_apply|cfg_euler|row_norm" -c 14 -o gpurun_out/prof_bw -f \
-  python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-extras > gpurun_out/ncu_bw_run.log 2>&1
+timeout 900 ncu --set full --clock-control none -k "regex:mel_stft|istft_frames|istft_ola|dwconv7_ln|grn_sumsq|grn_apply|cfg_euler|row_norm|ln_affine" -s 30 -c 30 -o gpurun_out/prof_bw -f \
+  python tools/ncu_bw.py > gpurun_out/ncu_bw_run.log 2>&1
 tail -2 gpurun_out/ncu_bw_run.log | cut -c1-200
 ls -la gpurun_out | tail -30
