@@ -23,7 +23,7 @@
 // Warp roles (384 threads = three warpgroups): warp 0 TMA producer, warp 1 MMA issuer / TMEM allocator, warps 2-3 idle;
 // warps 4..7 softmax WG0, warps 8..11 softmax WG1 (warp w touches TMEM lane quarter w % 4).  The softmax threads hold a
 // 128-score row AND its 64 packed probabilities in registers, so the register file is re-split with setmaxnreg: the
-// producer warpgroup drops to 64 registers per thread, the two softmax warpgroups grow to 224 (no spills).
+// producer warpgroup drops to 64 registers per thread, the two softmax warpgroups grow to 216 (no spills; 128 x 64 + 256 x 216 stays inside the 384 x 168 registers the CTA was launched with — setmaxnreg.inc can only draw on the CTA's own pool).
 #pragma once
 #include "common.cuh"
 #include "kparams.h"
@@ -281,7 +281,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnPar
     }
   }
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
     const int w = (warp - 4) >> 2;  // softmax warpgroup 0 / 1
     const int q = warp & 3;         // TMEM lane quarter
     const int row = q * 32 + int(lane_id());

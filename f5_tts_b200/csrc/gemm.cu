@@ -285,7 +285,7 @@ TileChoice pick_tile(long long rows, int batches, int n_out, int k, int epi, int
   const bool wide_ok = (epi == F5_EPI_F16 && (plain || gelu)) || ((epi == F5_EPI_RESID || epi == F5_EPI_QKV_ROPE) && plain);
   TileChoice best{128, 0};
   double best_cost = 1e30;
-  const int cand[5][2] = {{128, 0}, {192, 0}, {256, 0}, {128, 1}, {256, 1}};  // {192, 1}: instantiated, on request only
+  const int cand[6][2] = {{128, 0}, {192, 0}, {256, 0}, {128, 1}, {192, 1}, {256, 1}};
   for (const auto& c : cand) {
     const int bn = c[0], pair = c[1];
     if ((pair || bn == 192) && !wide_ok) continue;
