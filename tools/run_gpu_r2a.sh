@@ -3,6 +3,8 @@
 # exact_varlen, new parity tests, bench line.  Every stage runs in its own process (a device trap poisons a CUDA context).
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv | tee gpurun_out/gpu.txt
+echo "=== TS-form MMA layout probe"
+timeout 60 tools/microbench/ts_mma 2>&1 | tail -12 | tee gpurun_out/ts_mma.log
 echo "=== attention parity (kernel tests)"
 timeout 600 python -m pytest tests/test_gpu_kernels.py -q -m gpu -k "attention" -s 2>&1 | grep -v "^$" | tail -15 | tee gpurun_out/test_attn.log
 echo "=== attention timing: production build"
