@@ -87,7 +87,7 @@ static int launch_inst(const GemmPlan& pl, cudaStream_t s) {
   auto kern = gemm_tcgen05_kernel<BN, STAGES, EPI, ACT, CONV, PAIR, NORMA>;
   constexpr size_t smem = gemm_smem_bytes<BN, STAGES, PAIR>();
   if (int rc = configure_kernels()) return rc;
-  PdlLaunch L(pl.grid, dim3(gemm_threads(ACT)), smem, s, PAIR ? 2 : 1);
+  PdlLaunch L(pl.grid, dim3(gemm_threads(EPI, ACT)), smem, s, PAIR ? 2 : 1);
   if (int rc = check_cuda(cudaLaunchKernelEx(&L.cfg, kern, pl.tmA, pl.tmB, pl.tmC, pl.p), "gemm launch")) return rc;
   count_launch();
   return check_launch("gemm_tcgen05_kernel launch");

@@ -41,8 +41,12 @@ constexpr int kEpiBufs = 2;                     // one staging buffer per epilog
 // ~2x the instructions) get a second column group (measured FF1: 14.1 -> 12.4 us at M = 1876, 1025 -> 1196 TFLOP/s at
 // M = 15008); the plain / RoPE / reduce-add epilogues were not faster with eight warps (register cap 168, single TMEM
 // buffer) and keep four.
-__host__ __device__ constexpr int gemm_epi_groups(int act) { return act != ACT_NONE ? 2 : 1; }
-__host__ __device__ constexpr int gemm_threads(int act) { return 64 + 128 * gemm_epi_groups(act); }
+#ifdef F5_RESID_EG2  // experiment build: fp32 reduce-add epilogues on two column groups as well (tools/gemm_sweep.py A/B)
+__host__ __device__ constexpr int gemm_epi_groups(int epi, int act) { return (act != ACT_NONE || epi == EPI_RESID) ? 2 : 1; }
+#else
+__host__ __device__ constexpr int gemm_epi_groups(int /*epi*/, int act) { return act != ACT_NONE ? 2 : 1; }
+#endif
+__host__ __device__ constexpr int gemm_threads(int epi, int act) { return 64 + 128 * gemm_epi_groups(epi, act); }
 
 template <int BN, int STAGES, bool PAIR = false>
 constexpr size_t gemm_smem_bytes() {
@@ -306,7 +310,7 @@ __device__ __forceinline__ bool tile_is_padding(const GemmParams& p, int m0, int
 // each CTA's accumulator half lands in its own TMEM.  Shared-memory traffic per MMA cycle drops by 1/4 (BN = 256) —
 // the measured limiter of the single-CTA kernel (operand writes by TMA + reads by the tensor core > 128 B/clk).
 template <int BN, int STAGES, int EPI, int ACT, bool CONV, bool PAIR = false, bool NORMA = false>
-__global__ void __launch_bounds__(gemm_threads(ACT), 1)
+__global__ void __launch_bounds__(gemm_threads(EPI, ACT), 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
   static_assert(!(PAIR && CONV), "the conv schedule is single-CTA");
@@ -362,7 +366,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&acc_full[b], 1);
-      mbar_init(&acc_empty[b], (PAIR ? 2 : 1) * 128 * gemm_epi_groups(ACT));  // PAIR: both CTAs' epilogue threads arrive on the leader's barrier
+      mbar_init(&acc_empty[b], (PAIR ? 2 : 1) * 128 * gemm_epi_groups(EPI, ACT));  // PAIR: both CTAs' epilogue threads arrive on the leader's barrier
     }
     fence_mbar_init();
   }
@@ -480,7 +484,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // ===== epilogue: warps 2.. (4 * EG warps).  Warp w reads TMEM lane quarter w % 4 (rows); with EG = 2 column group
     // eg = (w - 2) / 4 takes every other 128-byte chunk of the tile, so two warps per scheduler hide each other's
     // latencies (a lone warp needs ~860 clk per 32-column piece for ~200 issue slots).
-    constexpr int EG = gemm_epi_groups(ACT);
+    constexpr int EG = gemm_epi_groups(EPI, ACT);
     constexpr int ETH = 128 * EG;  // epilogue threads
     const int q = warp & 3;
     const int eg = (EG == 2) ? (warp - 2) >> 2 : 0;

@@ -28,6 +28,9 @@ timeout 900 python bench.py --steps 5 --warmup 3 2> gpurun_out/bench.err | tee g
 tail -5 gpurun_out/bench.err
 echo "=== gemm sweep (M = 1876)"
 SWEEP_M=1876 timeout 600 python tools/gemm_sweep.py 2>&1 | tail -8 | tee gpurun_out/gemm_sweep.log
+echo "=== gemm sweep, experiment build: reduce-add epilogue on two column groups"
+F5_LIB=$PWD/f5_tts_b200/libf5tts_b200_eg2.so SWEEP_M=1876,15008 timeout 600 python tools/gemm_sweep.py 2>&1 | grep -E "out|FF2" | tail -8 | tee gpurun_out/gemm_sweep_eg2.log
+SWEEP_M=15008 timeout 600 python tools/gemm_sweep.py 2>&1 | tail -4 | tee gpurun_out/gemm_sweep_15008.log
 echo "=== ncu launch list"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 150 -c 400 --csv --log-file gpurun_out/launches.csv \
   python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-extras > gpurun_out/ncu_launch_run.log 2>&1
