@@ -99,12 +99,13 @@ __device__ __forceinline__ void ex2_poly2(uint64_t x2, float& e0, float& e1) {
 
 constexpr int kPolyOf8 = 3;  // element pairs (of every 8) whose 2^x runs on the FMA pipe instead of MUFU
 
-// 32 scores -> 16 packed fp16 pairs of exp2(s * sc - ms); FULL = every key of the chunk is valid (no masking code).
+// 32 scores -> 16 packed fp16 pairs of exp2(s * sc - ms).  Keys past the end of the sample carry a score of -inf (set by
+// the caller on the last tile), so there is ONE code path; a 32-key chunk that lies entirely past the end costs nothing.
 // POLY = pairs of every 8 computed with the polynomial (evenly interleaved with the MUFU ones).
-template <bool FULL, int POLY>
+template <int POLY>
 __device__ __forceinline__ void exp_pack32(const uint32_t (&r)[32], int col0, int kv_rem, uint64_t sc2, uint64_t nms2,
                                            uint64_t& sum2, uint32_t* pk) {
-  if (!FULL && col0 >= kv_rem) {  // warp-uniform: every key of this chunk is past the end of the sample -> P = 0
+  if (col0 >= kv_rem) {  // warp-uniform: every key of this chunk is past the end of the sample -> P = 0
 #pragma unroll
     for (int i = 0; i < 16; ++i) pk[i] = 0u;
     return;
@@ -122,37 +123,29 @@ __device__ __forceinline__ void exp_pack32(const uint32_t (&r)[32], int col0, in
       e0 = ex2_approx(x0);
       e1 = ex2_approx(x1);
     }
-    if (!FULL) {
-      if (col0 + 2 * i >= kv_rem) e0 = 0.f;
-      if (col0 + 2 * i + 1 >= kv_rem) e1 = 0.f;
-    }
     sum2 = f2_add(sum2, f2_pack(e0, e1));
     pk[i] = pack_half2(e0, e1);
   }
 }
 
-template <bool FULL>
 __device__ __forceinline__ float row_max128(const uint32_t (&r0)[32], const uint32_t (&r1)[32], const uint32_t (&r2)[32],
-                                            const uint32_t (&r3)[32], int kv_rem) {
+                                            const uint32_t (&r3)[32]) {
   float ma = -INFINITY, mb = -INFINITY;
-  if (FULL) {
 #pragma unroll
-    for (int i = 0; i < 32; i += 2) {
-      ma = fmax3(ma, __uint_as_float(r0[i]), __uint_as_float(r0[i + 1]));
-      mb = fmax3(mb, __uint_as_float(r1[i]), __uint_as_float(r1[i + 1]));
-      ma = fmax3(ma, __uint_as_float(r2[i]), __uint_as_float(r2[i + 1]));
-      mb = fmax3(mb, __uint_as_float(r3[i]), __uint_as_float(r3[i + 1]));
-    }
-  } else {
-#pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      if (i < kv_rem) ma = fmaxf(ma, __uint_as_float(r0[i]));
-      if (32 + i < kv_rem) mb = fmaxf(mb, __uint_as_float(r1[i]));
-      if (64 + i < kv_rem) ma = fmaxf(ma, __uint_as_float(r2[i]));
-      if (96 + i < kv_rem) mb = fmaxf(mb, __uint_as_float(r3[i]));
-    }
+  for (int i = 0; i < 32; i += 2) {
+    ma = fmax3(ma, __uint_as_float(r0[i]), __uint_as_float(r0[i + 1]));
+    mb = fmax3(mb, __uint_as_float(r1[i]), __uint_as_float(r1[i + 1]));
+    ma = fmax3(ma, __uint_as_float(r2[i]), __uint_as_float(r2[i + 1]));
+    mb = fmax3(mb, __uint_as_float(r3[i]), __uint_as_float(r3[i + 1]));
   }
   return fmaxf(ma, mb);
+}
+
+// scores of keys at or past kv_rem -> -inf (last key tile of a sample only)
+__device__ __forceinline__ void mask_tail32(uint32_t (&r)[32], int col0, int kv_rem) {
+#pragma unroll
+  for (int i = 0; i < 32; ++i)
+    if (col0 + i >= kv_rem) r[i] = 0xff800000u;
 }
 
 template <int POLY>
@@ -319,8 +312,13 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnPar
 #endif
       tc_fence_before();
       mbar_arrive(&s_free[w]);  // S_w is in registers: the tensor core may overwrite it with the next tile's scores
-      const bool full_tile = kv_rem >= kAttnBKV;  // warp-uniform
-      const float mx = full_tile ? row_max128<true>(r0, r1, r2, r3, kv_rem) : row_max128<false>(r0, r1, r2, r3, kv_rem);
+      if (kv_rem < kAttnBKV) {  // warp-uniform, last tile of the sample: one masking pass instead of a second code path
+        mask_tail32(r0, 0, kv_rem);
+        mask_tail32(r1, 32, kv_rem);
+        mask_tail32(r2, 64, kv_rem);
+        mask_tail32(r3, 96, kv_rem);
+      }
+      const float mx = row_max128(r0, r1, r2, r3);
       const float m_new = fmaxf(m_run, mx * p.scale_log2);
       // lazy rescale (warp-uniform decision because tcgen05.ld/st are warp-collective)
       const bool grow = (m_new - m_run) > 8.0f;  // also true on the first tile (m_run = -inf)
@@ -342,17 +340,10 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnPar
       const uint64_t nms2 = f2_pack(-m_run, -m_run);
       uint64_t sum2 = f2_pack(0.0f, 0.0f);
       uint32_t pa[32], pb[32];  // keys 0..63 / 64..127 as fp16 pairs = TMEM columns 0..31 / 32..63 of P_w
-      if (full_tile) {
-        exp_pack32<true, POLY>(r0, 0, kv_rem, sc2, nms2, sum2, pa);
-        exp_pack32<true, POLY>(r1, 32, kv_rem, sc2, nms2, sum2, pa + 16);
-        exp_pack32<true, POLY>(r2, 64, kv_rem, sc2, nms2, sum2, pb);
-        exp_pack32<true, POLY>(r3, 96, kv_rem, sc2, nms2, sum2, pb + 16);
-      } else {
-        exp_pack32<false, POLY>(r0, 0, kv_rem, sc2, nms2, sum2, pa);
-        exp_pack32<false, POLY>(r1, 32, kv_rem, sc2, nms2, sum2, pa + 16);
-        exp_pack32<false, POLY>(r2, 64, kv_rem, sc2, nms2, sum2, pb);
-        exp_pack32<false, POLY>(r3, 96, kv_rem, sc2, nms2, sum2, pb + 16);
-      }
+      exp_pack32<POLY>(r0, 0, kv_rem, sc2, nms2, sum2, pa);
+      exp_pack32<POLY>(r1, 32, kv_rem, sc2, nms2, sum2, pa + 16);
+      exp_pack32<POLY>(r2, 64, kv_rem, sc2, nms2, sum2, pb);
+      exp_pack32<POLY>(r3, 96, kv_rem, sc2, nms2, sum2, pb + 16);
       float ls0, ls1;
       f2_unpack(sum2, ls0, ls1);
       l_run = l_run * alpha + (ls0 + ls1);

@@ -82,7 +82,8 @@ def test_cfg2_full_nfe32_vs_reference(golden_dir):
         print(f"   step {k:2d}: B200 path {drift[k]:.3e}   reference's own fp16 path {ref16[k]:.3e}")
     final = rel(out, torch.from_numpy(z["out"]))
     print(f"   final mel (all rows) {final:.3e}   gate {TOL:.0e}")
-    assert torch.equal(out[:, :n_ref].float().cpu(), torch.from_numpy(z["out"])[:, :n_ref]), "prompt rows are copied"
+    # prompt rows are the prompt mel itself (cfm.py:221-223): CUDA mel kernel vs torchaudio on the CPU, fp32 rounding only
+    assert torch.allclose(out[:, :n_ref].float().cpu(), torch.from_numpy(z["out"])[:, :n_ref], atol=2e-4), "prompt rows"
     assert all(v <= TOL for v in drift.values()) and final <= TOL
     # fp32 state / residual / statistics: the B200 path must not drift more than the reference's fp16 path does
     assert drift[32] <= ref16[32]

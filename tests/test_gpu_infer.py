@@ -78,7 +78,9 @@ def expected_chunk(a, gen_text, y0):
     rms = float(torch.sqrt(torch.mean(torch.square(audio))))
     if rms < 0.1:
         audio = audio * 0.1 / rms
-    ref_text = REF_TEXT + " "  # preprocess_ref_audio_text (utils_infer.py:369-376): ends with "." -> one space added
+    # preprocess_ref_audio_text (utils_infer.py:369-376) appends " " after the final "."; infer_batch_process appends
+    # another one because the last character is a single byte (utils_infer.py:474-475)
+    ref_text = REF_TEXT + "  "
     tokens = infer.convert_char_to_pinyin([ref_text + gen_text])
     ids = list_str_to_idx(tokens, a["tts"].ema_model.vocab_char_map)
     ref_len = audio.shape[-1] // 256
@@ -99,7 +101,7 @@ def test_f5tts_infer_single_chunk(assets):
     assert sr == 24000 and a["tts"].seed == seed
     # the noise `sample` drew: first device randn after seed_everything(seed) (api.py:117-121, cfm.py:196-201)
     ref_len = 127987 // 256
-    duration = ref_len + int(ref_len / len((REF_TEXT + " ").encode()) * len(GEN_SHORT.encode()))
+    duration = ref_len + int(ref_len / len((REF_TEXT + "  ").encode()) * len(GEN_SHORT.encode()))
     api.seed_everything(seed)
     y0 = torch.randn(duration, 100, device=DEV, dtype=torch.float16).float().cpu()[None]
     w_ref, s_ref, dur, rl = expected_chunk(a, GEN_SHORT, y0)
@@ -123,7 +125,8 @@ def test_f5tts_infer_multi_chunk_shapes_and_files(assets, tmp_path):
     wav, sr, spec = a["tts"].infer(a["ref"], REF_TEXT, GEN_LONG, nfe_step=4, seed=7, file_wave=fw, file_spec=fs,
                                    show_info=lambda *_: None)
     ref_len = audio.shape[-1] // 256
-    durs = [ref_len + int(ref_len / len(ref_text.encode()) * len(c.encode()) / (0.3 if len(c.encode()) < 10 else 1.0))
+    rt2 = ref_text + " "  # infer_batch_process appends a second space (utils_infer.py:474-475)
+    durs = [ref_len + int(ref_len / len(rt2.encode()) * len(c.encode()) / (0.3 if len(c.encode()) < 10 else 1.0))
             for c in chunks]
     fade = int(0.15 * 24000)
     assert spec.shape == (100, sum(d - ref_len for d in durs))
