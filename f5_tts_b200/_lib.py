@@ -30,6 +30,7 @@ class GemmArgs(C.Structure):
         ("norm_x", c_void_p), ("norm_mode", c_int), ("norm_a", c_void_p), ("norm_b", c_void_p),
         ("norm_step_stride", c_ll), ("norm_counters", c_void_p), ("norm_eps", c_float),
         ("skip_padded_tiles", c_int),
+        ("done_counters", c_void_p), ("ready_counters", c_void_p), ("ready_target", c_int),
     ]
 
 
@@ -105,6 +106,8 @@ def lib():
         L.f5_launch_count.restype = C.c_ulonglong
         L.f5_gemm.argtypes = [c_void_p, c_void_p, C.POINTER(GemmArgs), c_void_p]
         L.f5_gemm_tile.argtypes = [C.POINTER(GemmArgs), C.POINTER(c_int), C.POINTER(c_int)]
+        L.f5_gemm_link_target.argtypes = [C.POINTER(GemmArgs)]
+        L.f5_gemm_link_target.restype = c_int
         L.f5_attention.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_float, c_void_p]
         L.f5_row_norm.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p]
         L.f5_mel_spectrogram.argtypes = [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p]
@@ -120,7 +123,7 @@ def lib():
         L.f5_sample.argtypes = [c_void_p, C.POINTER(SampleArgs), c_void_p, c_size_t, c_void_p]
         L.f5_sample_flops.argtypes = [c_void_p, c_int, c_int, c_int, c_float]
         L.f5_sample_flops.restype = C.c_double
-        for name in ("f5_gemm", "f5_gemm_tile", "f5_attention", "f5_row_norm", "f5_mel_spectrogram", "f5_vocos_decode",
+        for name in ("f5_gemm", "f5_gemm_tile", "f5_gemm_link_target", "f5_attention", "f5_row_norm", "f5_mel_spectrogram", "f5_vocos_decode",
                      "f5_engine_create", "f5_sample"):
             getattr(L, name).restype = c_int
         _lib = L
@@ -138,7 +141,7 @@ def launch_count() -> int:
 
 
 EXPORTED_SYMBOLS = [
-    "f5_version", "f5_last_error", "f5_launch_count", "f5_debug_gemm_trace", "f5_debug_attn_trace", "f5_gemm", "f5_gemm_tile", "f5_attention", "f5_row_norm", "f5_mel_spectrogram",
+    "f5_version", "f5_last_error", "f5_launch_count", "f5_debug_gemm_trace", "f5_debug_attn_trace", "f5_gemm", "f5_gemm_tile", "f5_gemm_link_target", "f5_attention", "f5_row_norm", "f5_mel_spectrogram",
     "f5_vocos_workspace_bytes", "f5_vocos_decode", "f5_engine_create", "f5_engine_destroy",
     "f5_sample_workspace_bytes", "f5_sample", "f5_sample_flops",
 ]

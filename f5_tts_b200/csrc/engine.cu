@@ -43,6 +43,7 @@ struct Layout {
   int* step_ptr;
   SampleIo* io;     // caller tensors + cfg scale of THIS call, read by the step kernels through the workspace
   int* norm_ctr;    // [2 * depth][ceil(M1 / 128)] row counters of the GEMMs that normalise their own A operand
+  int* link_ctr;    // [depth][ceil(M1 / 128)] tile counters of the FF1 -> FF2 hand-off (gemm.cuh: linked GEMMs)
   int norm_blocks;  // ceil(M1 / 128)
   float* dt;
   float* t_dev;
@@ -123,7 +124,8 @@ static void plan_layout(const f5_engine* e, Layout& L, void* ws, int B, int N, i
   L.step_ptr = bp.take<int>(64);
   L.io = bp.take<SampleIo>(1);
   L.norm_blocks = (int)((L.M1 + 127) / 128);
-  L.norm_ctr = bp.take<int>((size_t)2 * A.depth * L.norm_blocks);
+  L.norm_ctr = bp.take<int>((size_t)3 * A.depth * L.norm_blocks);  // + link_ctr, cleared together
+  L.link_ctr = L.norm_ctr + (size_t)2 * A.depth * L.norm_blocks;
   L.dt = bp.take<float>(steps + 1);
   L.t_dev = bp.take<float>(steps + 1);
   L.rope_cos = bp.take<float>((size_t)L.seq * 32);
@@ -354,6 +356,7 @@ int build_step_plans(f5_engine* e, const Layout& L, const f5_sample_args* sa, St
       a.norm_step_stride = 0;
     }
   };
+  int ff1_link_target = 0;
   for (int i = 0; i < A.depth; ++i) {
     const f5_layer_weights& lw = W.layers[i];
     if (!dit && lw.w_skip) {
@@ -398,6 +401,8 @@ int build_step_plans(f5_engine* e, const Layout& L, const f5_sample_args* sa, St
       a.out = L.g;
       a.ldo = F;
       varlen(a);
+      a.done_counters = L.link_ctr + (size_t)i * L.norm_blocks;  // FF2 starts block by block (linked GEMMs)
+      ff1_link_target = f5_gemm_link_target(&a);
       RC(gemm_plan(&P.ff1[i], L.a, lw.w_ff1, &a));
     }
     {
@@ -411,6 +416,9 @@ int build_step_plans(f5_engine* e, const Layout& L, const f5_sample_args* sa, St
         a.gate_step_stride = modS;
       }
       varlen(a);
+      a.ready_counters = L.link_ctr + (size_t)i * L.norm_blocks;
+      a.ready_target = ff1_link_target;
+      a.step_ptr = L.step_ptr;
       RC(gemm_plan(&P.ff2[i], L.g, lw.w_ff2, &a));
     }
   }
@@ -519,7 +527,7 @@ int run_prologue(f5_engine* e, const Layout& L, const f5_sample_args* sa, cudaSt
   RC(check_cuda(cudaMemcpyAsync(L.dt, dt.data(), sizeof(float) * (S + 1), cudaMemcpyHostToDevice, s), "dt h2d"));
   RC(check_cuda(cudaMemcpyAsync(L.t_dev, sa->t, sizeof(float) * (S + 1), cudaMemcpyHostToDevice, s), "t h2d"));
   RC(check_cuda(cudaMemsetAsync(L.step_ptr, 0, sizeof(int) * 64, s), "step memset"));
-  RC(check_cuda(cudaMemsetAsync(L.norm_ctr, 0, sizeof(int) * 2 * A.depth * L.norm_blocks, s), "norm counters"));
+  RC(check_cuda(cudaMemsetAsync(L.norm_ctr, 0, sizeof(int) * 3 * A.depth * L.norm_blocks, s), "block counters"));
   SampleIo io{sa->y, sa->trajectory, sa->cfg_strength};
   RC(check_cuda(cudaMemcpyAsync(L.io, &io, sizeof(io), cudaMemcpyHostToDevice, s), "io h2d"));
   if (masked) {

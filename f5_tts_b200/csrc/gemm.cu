@@ -378,6 +378,9 @@ int gemm_plan(GemmPlan* pl, const void* A, const void* W, const f5_gemm_args* a)
   p.norm_mode = a->norm_mode;
   p.norm_d = a->k;
   p.norm_eps = a->norm_eps;
+  p.done_ctr = (a->epi != F5_EPI_F32 && !conv) ? a->done_counters : nullptr;  // staged epilogues only
+  p.ready_ctr = !conv && a->batches == 1 ? a->ready_counters : nullptr;
+  p.ready_target = a->ready_target;
 #ifdef F5_TRACE  // instrumented build only: kernel skip modes (wrong results) and the per-CTA timestamp trace
   {
     static int dbg = -1;
@@ -479,6 +482,13 @@ int f5_gemm_tile(const f5_gemm_args* args, int* bn, int* cta_pair) {
   *bn = b;
   *cta_pair = (args->conv_taps == 0 && pr && args->epi != F5_EPI_F32 && b >= 128) ? 1 : 0;
   return 0;
+}
+
+int f5_gemm_link_target(const f5_gemm_args* args) {
+  if (!args) return -1;
+  int bn = 0, pair = 0;
+  if (f5_gemm_tile(args, &bn, &pair)) return -1;
+  return ((args->n_out + bn - 1) / bn) * f5::gemm_epi_groups(args->epi, args->act);
 }
 
 int f5_gemm(const void* A, const void* W, const f5_gemm_args* args, f5_stream_t stream) {

@@ -274,12 +274,33 @@ __device__ __forceinline__ void norm_rows_phase(const GemmParams& p, int gw, int
   }
 }
 
-// TMA producer side: the 128-row block `mblk` of the A buffer is complete for this step
+// TMA producer side: spin (acquire) until counter `c` has reached `target`, then order the async-proxy reads after it
+__device__ __forceinline__ void wait_counter(const int* c, int target, int mblk);
+
+// the 128-row block `mblk` of the A buffer has been normalised for this step
 __device__ __forceinline__ void norm_wait_block(const GemmParams& p, int mblk, int epoch) {
   if (mblk * kBM >= p.rows) return;  // tile past the end (zero-filled by TMA)
   const int nrows = min(kBM, p.rows - mblk * kBM);
-  const int target = nrows * (epoch + 1);
-  const int* c = p.norm_ctr + mblk;
+  wait_counter(p.norm_ctr + mblk, nrows * (epoch + 1), mblk);
+}
+
+// ---- linked GEMMs ---------------------------------------------------------------------------------------------------
+// FF1 (240 tiles at cfg2) runs 1.6 rounds over 148 SMs: in its second round 56 SMs are idle, and FF2 (120 tiles, one
+// round) could not start before the whole FF1 grid had drained.  Linked, the producer GEMM publishes one counter per
+// 128-row block of its output (+1 per finished tile and epilogue column group, after the bulk stores of the tile have
+// completed), and the consumer — launched programmatically early, it never executes griddepcontrol.wait — loads a block
+// of its A operand as soon as that block's counter says all of the producer's column tiles are in memory.  Its CTAs
+// take over the SMs the producer's one-tile CTAs vacate and work on the blocks the producer's first round finished.
+// Safe without the grid-wide wait: everything else the consumer reads (weights, bias, gate row, step counter) predates
+// the producer, and the residual rows it reduce-adds into were last READ by the producer's own normalisation phase of
+// the same block, which precedes the producer's tiles of that block.  No deadlock: the consumer can only be scheduled
+// after every producer CTA is resident (programmatic launch), and the producer is a persistent grid.
+__device__ __forceinline__ void link_wait_block(const GemmParams& p, int mblk, int epoch) {
+  if (mblk * kBM >= p.rows) return;
+  wait_counter(p.ready_ctr + mblk, p.ready_target * (epoch + 1), mblk);
+}
+
+__device__ __forceinline__ void wait_counter(const int* c, int target, int mblk) {
   int v;
   long long t0 = 0;
   for (;;) {
@@ -287,7 +308,7 @@ __device__ __forceinline__ void norm_wait_block(const GemmParams& p, int mblk, i
     if (v >= target) break;
     if (t0 == 0) t0 = clock64();
     if (clock64() - t0 > F5_SPIN_TIMEOUT_CYCLES) {
-      printf("f5: norm block wait timeout block %d mblk %d have %d want %d\n", blockIdx.x, mblk, v, target);
+      printf("f5: block counter wait timeout block %d mblk %d have %d want %d\n", blockIdx.x, mblk, v, target);
       __trap();
     }
   }
@@ -385,7 +406,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   // Programmatic dependent launch: everything above overlapped the predecessor's tail.  The producer thread goes one
   // step further (below): W tiles are weights, not produced by the predecessor, so their TMA loads are issued BEFORE
   // the dependency wait and the DRAM latency of the first STAGES k-blocks hides under the predecessor too.
-  if (warp != 0) pdl_wait();  // predecessor kernel finished: its outputs (our A operand, residual, ...) are visible
+  // linked consumer (ready_ctr): no grid-wide wait at all — its A operand arrives block by block (link_wait_block)
+  const bool linked_in = p.ready_ctr != nullptr;
+  if (warp != 0 && !linked_in) pdl_wait();  // predecessor kernel finished: its outputs (A operand, residual, ...) are visible
   pdl_launch_dependents();    // let the next kernel's prologue overlap our tail
 #ifdef F5_TRACE
   if (ts && threadIdx.x == 0) ts[2] = clock64();  // setup done
@@ -418,14 +441,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           load_w(int(kb), int(kb), (cta_id % tiles_n) * BN);
         }
       }
-      pdl_wait();
-      const int epoch = (NORMA && p.step_ptr) ? *p.step_ptr : 0;
+      if (!linked_in) pdl_wait();
+      const int epoch = ((NORMA || linked_in) && p.step_ptr) ? *p.step_ptr : 0;
       for (int t = cta_id; t < num_tiles; t += cta_step) {
         const int n0 = (t % tiles_n) * BN;
         const int m0 = ((t / tiles_n) % tiles_m) * TM + int(rank) * kBM;
         const int bz = t / (tiles_n * tiles_m);
         if (tile_is_padding<CONV>(p, ((t / tiles_n) % tiles_m) * TM, TM, bz)) continue;
         if (NORMA) norm_wait_block(p, m0 / kBM, epoch);  // the epilogue warps of all CTAs are producing this block
+        if (linked_in && !tile_is_padding<CONV>(p, m0, kBM, bz)) link_wait_block(p, m0 / kBM, epoch);
         for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
@@ -668,6 +692,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               tma_store_commit();
             }
           }
+        }
+        if (p.done_ctr != nullptr && issuer && m0 < p.rows) {
+          // linked producer: this group's bulk stores of the tile are complete (not merely read out of shared memory)
+          tma_store_wait_all();
+          asm volatile("fence.proxy.async.global;" ::: "memory");
+          __threadfence();
+          atomicAdd(p.done_ctr + m0 / kBM, 1);
         }
       }
       tc_fence_before();
