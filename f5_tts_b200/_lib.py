@@ -27,8 +27,6 @@ class GemmArgs(C.Structure):
         ("gate", c_void_p), ("step_ptr", c_void_p), ("gate_step_stride", c_ll), ("row_len", c_void_p),
         ("seq", c_int), ("rope_cos", c_void_p), ("rope_sin", c_void_p), ("inner", c_int), ("pe_heads", c_int),
         ("weights_static", c_int),
-        ("norm_x", c_void_p), ("norm_mode", c_int), ("norm_a", c_void_p), ("norm_b", c_void_p),
-        ("norm_step_stride", c_ll), ("norm_counters", c_void_p), ("norm_eps", c_float),
         ("skip_padded_tiles", c_int),
         ("done_counters", c_void_p), ("ready_counters", c_void_p), ("ready_target", c_int),
     ]

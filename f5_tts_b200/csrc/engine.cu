@@ -42,7 +42,6 @@ struct Layout {
   // common
   int* step_ptr;
   SampleIo* io;     // caller tensors + cfg scale of THIS call, read by the step kernels through the workspace
-  int* norm_ctr;    // [2 * depth][ceil(M1 / 128)] row counters of the GEMMs that normalise their own A operand
   int* link_ctr;    // [depth][ceil(M1 / 128)] tile counters of the FF1 -> FF2 hand-off (gemm.cuh: linked GEMMs)
   int norm_blocks;  // ceil(M1 / 128)
   float* dt;
@@ -124,8 +123,7 @@ static void plan_layout(const f5_engine* e, Layout& L, void* ws, int B, int N, i
   L.step_ptr = bp.take<int>(64);
   L.io = bp.take<SampleIo>(1);
   L.norm_blocks = (int)((L.M1 + 127) / 128);
-  L.norm_ctr = bp.take<int>((size_t)3 * A.depth * L.norm_blocks);  // + link_ctr, cleared together
-  L.link_ctr = L.norm_ctr + (size_t)2 * A.depth * L.norm_blocks;
+  L.link_ctr = bp.take<int>((size_t)A.depth * L.norm_blocks);
   L.dt = bp.take<float>(steps + 1);
   L.t_dev = bp.take<float>(steps + 1);
   L.rope_cos = bp.take<float>((size_t)L.seq * 32);
@@ -337,25 +335,6 @@ int build_step_plans(f5_engine* e, const Layout& L, const f5_sample_args* sa, St
     a.seq = L.seq;
     a.skip_padded_tiles = 1;
   };
-  // The row normalisation in front of the QKV and FF1 projections runs INSIDE those GEMMs (gemm.cuh: NORMA): x (fp32
-  // residual stream) -> L.a (fp16) by the GEMM's own epilogue warps, consumed 128-row block by 128-row block.
-  auto fuse_norm = [&](f5_gemm_args& a, int layer, int which) {
-    a.norm_x = L.x;
-    a.norm_eps = 1e-6f;
-    a.norm_counters = L.norm_ctr + (size_t)(2 * layer + which) * L.norm_blocks;
-    a.step_ptr = L.step_ptr;
-    if (dit) {
-      const float* m = L.mod + (size_t)layer * 6 * D + (which ? 3 * D : 0);  // shift, scale (modules.py:323)
-      a.norm_mode = 0;
-      a.norm_a = m + D;
-      a.norm_b = m;
-      a.norm_step_stride = modS;
-    } else {
-      a.norm_mode = 2;
-      a.norm_a = which ? W.layers[layer].g_ff : W.layers[layer].g_attn;
-      a.norm_step_stride = 0;
-    }
-  };
   int ff1_link_target = 0;
   for (int i = 0; i < A.depth; ++i) {
     const f5_layer_weights& lw = W.layers[i];
@@ -367,7 +346,6 @@ int build_step_plans(f5_engine* e, const Layout& L, const f5_sample_args* sa, St
     }
     {
       f5_gemm_args a = base_args(L.M1, 3 * inner, D, D, D, kAutoTile, F5_EPI_QKV_ROPE, F5_ACT_NONE);
-      fuse_norm(a, i, 0);  // attn_norm (AdaLN: scale_msa, shift_msa / RMSNorm g) inside the QKV projection
       a.bias = lw.b_qkv;
       a.out = L.qkv;
       a.ldo = 3 * inner;
@@ -396,13 +374,14 @@ int build_step_plans(f5_engine* e, const Layout& L, const f5_sample_args* sa, St
     }
     {
       f5_gemm_args a = base_args(L.M1, F, D, D, D, kAutoTile, F5_EPI_F16, F5_ACT_GELU_TANH);
-      fuse_norm(a, i, 1);  // ff_norm (scale_mlp, shift_mlp / RMSNorm g) inside the first feed-forward projection
       a.bias = lw.b_ff1;
       a.out = L.g;
       a.ldo = F;
       varlen(a);
+#ifndef F5_NO_LINK
       a.done_counters = L.link_ctr + (size_t)i * L.norm_blocks;  // FF2 starts block by block (linked GEMMs)
       ff1_link_target = f5_gemm_link_target(&a);
+#endif
       RC(gemm_plan(&P.ff1[i], L.a, lw.w_ff1, &a));
     }
     {
@@ -416,9 +395,11 @@ int build_step_plans(f5_engine* e, const Layout& L, const f5_sample_args* sa, St
         a.gate_step_stride = modS;
       }
       varlen(a);
+#ifndef F5_NO_LINK
       a.ready_counters = L.link_ctr + (size_t)i * L.norm_blocks;
       a.ready_target = ff1_link_target;
       a.step_ptr = L.step_ptr;
+#endif
       RC(gemm_plan(&P.ff2[i], L.g, lw.w_ff2, &a));
     }
   }
@@ -475,7 +456,11 @@ int run_step(f5_engine* e, const Layout& L, const f5_sample_args* sa, const Step
   if (!dit) RC(run_prepend_time_token(L.x, L.h0, L.temb, L.step_ptr, L.N, D, L.M1, s));
   const int half = A.depth / 2;
   for (int i = 0; i < A.depth; ++i) {
-    if (!dit) {
+    const f5_layer_weights& lw = e->w.layers[i];
+    if (dit) {
+      const float* m = L.mod + (size_t)i * 6 * D;
+      RC(norm_mod(e, L, L.x, L.M1, 0, m + D, m, true, s));  // scale_msa, shift_msa
+    } else {
       if (i < half) {
         RC(check_cuda(cudaMemcpyAsync(L.skips[i], L.x, sizeof(float) * L.M1 * D, cudaMemcpyDeviceToDevice, s),
                       "skip copy"));
@@ -483,11 +468,18 @@ int run_step(f5_engine* e, const Layout& L, const f5_sample_args* sa, const Step
         RC(run_concat_half(L.x, L.skips[A.depth - 1 - i], L.cat, L.M1, D, s));
         RC(gemm_run(P.skip[i], s));
       }
+      RC(norm_mod(e, L, L.x, L.M1, 2, lw.g_attn, nullptr, false, s));
     }
-    if (!diag_skip("qkv")) RC(gemm_run(P.qkv[i], s));  // attn_norm fused (NORMA)
+    if (!diag_skip("qkv")) RC(gemm_run(P.qkv[i], s));
     if (!diag_skip("attn")) RC(attn_run(P.attn[0], s));
     if (!diag_skip("out")) RC(gemm_run(P.oproj[i], s));
-    if (!diag_skip("ff1")) RC(gemm_run(P.ff1[i], s));  // ff_norm fused (NORMA)
+    if (dit) {
+      const float* m = L.mod + (size_t)i * 6 * D;
+      RC(norm_mod(e, L, L.x, L.M1, 0, m + 4 * D, m + 3 * D, true, s));  // scale_mlp, shift_mlp
+    } else {
+      RC(norm_mod(e, L, L.x, L.M1, 2, lw.g_ff, nullptr, false, s));
+    }
+    if (!diag_skip("ff1")) RC(gemm_run(P.ff1[i], s));
     if (!diag_skip("ff2")) RC(gemm_run(P.ff2[i], s));
   }
   if (dit) {
@@ -527,7 +519,7 @@ int run_prologue(f5_engine* e, const Layout& L, const f5_sample_args* sa, cudaSt
   RC(check_cuda(cudaMemcpyAsync(L.dt, dt.data(), sizeof(float) * (S + 1), cudaMemcpyHostToDevice, s), "dt h2d"));
   RC(check_cuda(cudaMemcpyAsync(L.t_dev, sa->t, sizeof(float) * (S + 1), cudaMemcpyHostToDevice, s), "t h2d"));
   RC(check_cuda(cudaMemsetAsync(L.step_ptr, 0, sizeof(int) * 64, s), "step memset"));
-  RC(check_cuda(cudaMemsetAsync(L.norm_ctr, 0, sizeof(int) * 3 * A.depth * L.norm_blocks, s), "block counters"));
+  RC(check_cuda(cudaMemsetAsync(L.link_ctr, 0, sizeof(int) * A.depth * L.norm_blocks, s), "block counters"));
   SampleIo io{sa->y, sa->trajectory, sa->cfg_strength};
   RC(check_cuda(cudaMemcpyAsync(L.io, &io, sizeof(io), cudaMemcpyHostToDevice, s), "io h2d"));
   if (masked) {

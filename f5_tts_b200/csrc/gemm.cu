@@ -82,9 +82,9 @@ int encode_tmap(CUtensorMap* m, int is_f32, const void* ptr, uint64_t d0, uint64
 int configure_kernels();
 int num_sms();
 
-template <int BN, int STAGES, int EPI, int ACT, bool CONV, bool PAIR = false, bool NORMA = false>
+template <int BN, int STAGES, int EPI, int ACT, bool CONV, bool PAIR = false>
 static int launch_inst(const GemmPlan& pl, cudaStream_t s) {
-  auto kern = gemm_tcgen05_kernel<BN, STAGES, EPI, ACT, CONV, PAIR, NORMA>;
+  auto kern = gemm_tcgen05_kernel<BN, STAGES, EPI, ACT, CONV, PAIR>;
   constexpr size_t smem = gemm_smem_bytes<BN, STAGES, PAIR>();
   if (int rc = configure_kernels()) return rc;
   PdlLaunch L(pl.grid, dim3(gemm_threads(EPI, ACT)), smem, s, PAIR ? 2 : 1);
@@ -93,9 +93,9 @@ static int launch_inst(const GemmPlan& pl, cudaStream_t s) {
   return check_launch("gemm_tcgen05_kernel launch");
 }
 
-template <int BN, int STAGES, int EPI, int ACT, bool CONV, bool PAIR = false, bool NORMA = false>
+template <int BN, int STAGES, int EPI, int ACT, bool CONV, bool PAIR = false>
 static int configure_inst() {
-  auto kern = gemm_tcgen05_kernel<BN, STAGES, EPI, ACT, CONV, PAIR, NORMA>;
+  auto kern = gemm_tcgen05_kernel<BN, STAGES, EPI, ACT, CONV, PAIR>;
   constexpr size_t smem = gemm_smem_bytes<BN, STAGES, PAIR>();
   if (int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                           "cudaFuncSetAttribute(gemm smem)"))
@@ -105,29 +105,11 @@ static int configure_inst() {
 }
 
 #define F5_GEMM_CASE(BN_, ST_, EPI_, ACT_, CONV_)                                                                   \
-  if (!pl.pair && !pl.norma && pl.bn == BN_ && pl.epi == EPI_ && pl.act == ACT_ && (pl.conv != 0) == CONV_)        \
+  if (!pl.pair && pl.bn == BN_ && pl.epi == EPI_ && pl.act == ACT_ && (pl.conv != 0) == CONV_)        \
     return launch_inst<BN_, ST_, EPI_, ACT_, CONV_>(pl, s);
 #define F5_GEMM_PAIR_CASE(BN_, ST_, EPI_, ACT_)                                                  \
-  if (pl.pair && !pl.norma && pl.bn == BN_ && pl.epi == EPI_ && pl.act == ACT_ && !pl.conv)     \
+  if (pl.pair && pl.bn == BN_ && pl.epi == EPI_ && pl.act == ACT_ && !pl.conv)     \
     return launch_inst<BN_, ST_, EPI_, ACT_, false, true>(pl, s);
-// NORMA: the kernel normalises its own A operand (QKV and FF1 projections)
-#define F5_GEMM_NORMA_CASE(BN_, ST_, EPI_, ACT_, PAIR_)                                                    \
-  if (pl.norma && (pl.pair != 0) == PAIR_ && pl.bn == BN_ && pl.epi == EPI_ && pl.act == ACT_ && !pl.conv) \
-    return launch_inst<BN_, ST_, EPI_, ACT_, false, PAIR_, true>(pl, s);
-#define F5_GEMM_NORMA_LIST(X)              \
-  X(128, 5, EPI_QKV_ROPE, ACT_NONE, false) \
-  X(192, 4, EPI_QKV_ROPE, ACT_NONE, false) \
-  X(256, 3, EPI_QKV_ROPE, ACT_NONE, false) \
-  X(256, 5, EPI_QKV_ROPE, ACT_NONE, true)  \
-  X(192, 6, EPI_QKV_ROPE, ACT_NONE, true)  \
-  X(128, 6, EPI_QKV_ROPE, ACT_NONE, true)  \
-  X(128, 5, EPI_F16, ACT_GELU_TANH, false) \
-  X(192, 4, EPI_F16, ACT_GELU_TANH, false) \
-  X(256, 3, EPI_F16, ACT_GELU_TANH, false) \
-  X(256, 5, EPI_F16, ACT_GELU_TANH, true)  \
-  X(192, 6, EPI_F16, ACT_GELU_TANH, true)  \
-  X(128, 6, EPI_F16, ACT_GELU_TANH, true)
-
 // cudaFuncSetAttribute is per device: the configured flag and the SM count are tracked per device ordinal, so one
 // process may drive engines on several GPUs.
 namespace {
@@ -184,10 +166,6 @@ int configure_kernels() {
   if (int rc = configure_inst<128, 6, EPI_F16, ACT_GELU_TANH, false, true>()) return rc;
   if (int rc = configure_inst<128, 6, EPI_RESID, ACT_NONE, false, true>()) return rc;
   if (int rc = configure_inst<128, 6, EPI_QKV_ROPE, ACT_NONE, false, true>()) return rc;
-#define F5_CFG_NORMA(BN_, ST_, EPI_, ACT_, PAIR_) \
-  if (int rc = configure_inst<BN_, ST_, EPI_, ACT_, false, PAIR_, true>()) return rc;
-  F5_GEMM_NORMA_LIST(F5_CFG_NORMA)
-#undef F5_CFG_NORMA
   if (int rc = attn_configure()) return rc;
   g_dev[dev].configured = true;
   return 0;
@@ -252,7 +230,6 @@ int gemm_run(const GemmPlan& pl, cudaStream_t s) {
   F5_GEMM_PAIR_CASE(128, 6, EPI_F16, ACT_GELU_TANH)
   F5_GEMM_PAIR_CASE(128, 6, EPI_RESID, ACT_NONE)
   F5_GEMM_PAIR_CASE(128, 6, EPI_QKV_ROPE, ACT_NONE)
-  F5_GEMM_NORMA_LIST(F5_GEMM_NORMA_CASE)
   set_error("gemm: no kernel instantiated for bn=%d epi=%d act=%d conv=%d pair=%d", pl.bn, pl.epi, pl.act, pl.conv, pl.pair);
   return -6;
 }
@@ -336,17 +313,6 @@ int gemm_plan(GemmPlan* pl, const void* A, const void* W, const f5_gemm_args* a)
   pl->act = a->act;
   pl->conv = conv ? 1 : 0;
   pl->pair = (!conv && want_pair && a->epi != F5_EPI_F32 && bn >= 128) ? 1 : 0;
-  pl->norma = a->norm_x != nullptr ? 1 : 0;
-  if (pl->norma) {
-    const bool epi_ok = (a->epi == F5_EPI_QKV_ROPE && a->act == F5_ACT_NONE) || (a->epi == F5_EPI_F16 && a->act == F5_ACT_GELU_TANH);
-    if (conv || a->batches != 1 || !epi_ok || bn == 64 || a->k % 128 || a->k > 1024 || a->lda != a->k ||
-        a->norm_counters == nullptr || a->norm_a == nullptr || (a->norm_mode != 0 && a->norm_mode != 2) ||
-        (a->norm_mode == 0 && a->norm_b == nullptr)) {
-      set_error("gemm: fused A normalisation needs a plain single-batch GEMM with k %% 128 == 0, k <= 1024, lda == k, "
-                "tile width >= 128, the QKV_ROPE or F16+GELU_TANH epilogue, mode 0|2 and counters");
-      return -1;
-    }
-  }
   GemmParams& p = pl->p;
   p.rows = a->rows;
   p.n_out = a->n_out;
@@ -369,15 +335,6 @@ int gemm_plan(GemmPlan* pl, const void* A, const void* W, const f5_gemm_args* a)
   p.skip_pad = (a->skip_padded_tiles && a->row_len != nullptr && a->seq > 0 && (conv || a->batches == 1)) ? 1 : 0;
   // a prefetched W tile belongs to the CTA's first tile: not known to be computed when padded tiles are skipped
   p.w_prefetch = (a->weights_static && !p.skip_pad) ? 1 : 0;
-  p.norm_x = a->norm_x;
-  p.norm_out = reinterpret_cast<__half*>(const_cast<void*>(A));
-  p.norm_a = a->norm_a;
-  p.norm_b = a->norm_b;
-  p.norm_step_stride = a->norm_step_stride;
-  p.norm_ctr = a->norm_counters;
-  p.norm_mode = a->norm_mode;
-  p.norm_d = a->k;
-  p.norm_eps = a->norm_eps;
   p.done_ctr = (a->epi != F5_EPI_F32 && !conv) ? a->done_counters : nullptr;  // staged epilogues only
   p.ready_ctr = !conv && a->batches == 1 ? a->ready_counters : nullptr;
   p.ready_target = a->ready_target;

@@ -175,114 +175,8 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
   }
 }
 
-// ---- fused A-operand normalisation (NORMA kernels) -------------------------------------------------------------
-// The AdaLN / RMS row normalisation that precedes the QKV and FF1 projections used to be a kernel of its own between
-// two GEMMs: two grid-wide dependency hand-offs (~1.5 us each) around ~2 us of L2-latency-bound work, 44 times per NFE
-// step.  A NORMA GEMM does the normalisation itself: before their first tile, the epilogue warps of ALL its CTAs
-// normalise the rows of x (fp32, L2 resident) into the fp16 A buffer, block of 128 rows by block of 128 rows, and
-// publish per-block row counters (release); the TMA producer of a tile waits (acquire) only for the 128-row block it
-// is about to load and orders its async-proxy reads after the generic-proxy writes with fence.proxy.async.  Weight
-// tiles stream in meanwhile.  Counters are cumulative over the steps of one sample() call (target = rows x (step + 1)),
-// so a replayed CUDA graph needs no reset.
-__device__ __forceinline__ void norm_rows_phase(const GemmParams& p, int gw, int total_warps) {
-  const int lane = int(lane_id());
-  const int nv = p.norm_d >> 7;  // float4 per lane (norm_d multiple of 128, <= 1024)
-  const long long so = p.step_ptr ? (long long)(*p.step_ptr) * p.norm_step_stride : 0;
-  float4 ga[8], gb[8];
-  const float4* A4 = reinterpret_cast<const float4*>(p.norm_a + so);
-  const float4* B4 = p.norm_mode == 0 ? reinterpret_cast<const float4*>(p.norm_b + so) : nullptr;
-#pragma unroll
-  for (int i = 0; i < 8; ++i)
-    if (i < nv) {
-      ga[i] = __ldg(A4 + i * 32 + lane);
-      if (p.norm_mode == 0) {
-        gb[i] = __ldg(B4 + i * 32 + lane);
-        ga[i].x += 1.f, ga[i].y += 1.f, ga[i].z += 1.f, ga[i].w += 1.f;
-      }
-    }
-  const float inv_d = 1.0f / float(p.norm_d);
-  float4 v[8];
-  int r = gw;
-  if (r < p.rows) {
-    const float4* xr = reinterpret_cast<const float4*>(p.norm_x + (long long)r * p.norm_d);
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-      if (i < nv) v[i] = xr[i * 32 + lane];
-  }
-  // No fence inside the row loop: a release per row costs a round trip to L2 each (measured: +11 us per GEMM with a
-  // fence after every row); the rows of this warp are published together after the loop.
-  while (r < p.rows) {
-    const int rn = r + total_warps;
-    float4 vn[8];
-    if (rn < p.rows) {  // next row of this warp: in flight while the current one is reduced
-      const float4* xr = reinterpret_cast<const float4*>(p.norm_x + (long long)rn * p.norm_d);
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-        if (i < nv) vn[i] = xr[i * 32 + lane];
-    }
-    float s = 0.f, mean = 0.f, rstd;
-    if (p.norm_mode == 0) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-        if (i < nv) s += v[i].x + v[i].y + v[i].z + v[i].w;
-      mean = warp_sum(s) * inv_d;
-      float q = 0.f;
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-        if (i < nv) {
-          const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
-          q += a * a + b * b + c * c + d * d;
-        }
-      rstd = rsqrtf(warp_sum(q) * inv_d + p.norm_eps);
-    } else {
-      float q = 0.f;
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-        if (i < nv) q += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
-      rstd = sqrtf(float(p.norm_d)) / fmaxf(sqrtf(warp_sum(q)), 1e-12f);
-    }
-    uint2* o = reinterpret_cast<uint2*>(p.norm_out + (long long)r * p.norm_d);
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-      if (i < nv) {
-        const float4 a = ga[i];
-        float4 y;
-        if (p.norm_mode == 0) {
-          const float4 b = gb[i];
-          y.x = (v[i].x - mean) * rstd * a.x + b.x;
-          y.y = (v[i].y - mean) * rstd * a.y + b.y;
-          y.z = (v[i].z - mean) * rstd * a.z + b.z;
-          y.w = (v[i].w - mean) * rstd * a.w + b.w;
-        } else {
-          y.x = v[i].x * rstd * a.x;
-          y.y = v[i].y * rstd * a.y;
-          y.z = v[i].z * rstd * a.z;
-          y.w = v[i].w * rstd * a.w;
-        }
-        o[i * 32 + lane] = make_uint2(pack_half2(y.x, y.y), pack_half2(y.z, y.w));
-      }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = vn[i];
-    r = rn;
-  }
-  // publish: generic-proxy writes -> visible to TMA (async proxy) reads, then ONE gpu-scope release for all rows of the warp
-  asm volatile("fence.proxy.async.global;" ::: "memory");
-  __syncwarp();
-  if (lane == 0 && gw < p.rows) {
-    __threadfence();
-    for (int rr = gw; rr < p.rows; rr += total_warps) atomicAdd(p.norm_ctr + (rr >> 7), 1);
-  }
-}
-
 // TMA producer side: spin (acquire) until counter `c` has reached `target`, then order the async-proxy reads after it
 __device__ __forceinline__ void wait_counter(const int* c, int target, int mblk);
-
-// the 128-row block `mblk` of the A buffer has been normalised for this step
-__device__ __forceinline__ void norm_wait_block(const GemmParams& p, int mblk, int epoch) {
-  if (mblk * kBM >= p.rows) return;  // tile past the end (zero-filled by TMA)
-  const int nrows = min(kBM, p.rows - mblk * kBM);
-  wait_counter(p.norm_ctr + mblk, nrows * (epoch + 1), mblk);
-}
 
 // ---- linked GEMMs ---------------------------------------------------------------------------------------------------
 // FF1 (240 tiles at cfg2) runs 1.6 rounds over 148 SMs: in its second round 56 SMs are idle, and FF2 (120 tiles, one
@@ -292,8 +186,8 @@ __device__ __forceinline__ void norm_wait_block(const GemmParams& p, int mblk, i
 // of its A operand as soon as that block's counter says all of the producer's column tiles are in memory.  Its CTAs
 // take over the SMs the producer's one-tile CTAs vacate and work on the blocks the producer's first round finished.
 // Safe without the grid-wide wait: everything else the consumer reads (weights, bias, gate row, step counter) predates
-// the producer, and the residual rows it reduce-adds into were last READ by the producer's own normalisation phase of
-// the same block, which precedes the producer's tiles of that block.  No deadlock: the consumer can only be scheduled
+// the producer, and the residual rows it reduce-adds into were last READ by the row-norm kernel in front of the
+// producer, which the producer itself waited for.  No deadlock: the consumer can only be scheduled
 // after every producer CTA is resident (programmatic launch), and the producer is a persistent grid.
 __device__ __forceinline__ void link_wait_block(const GemmParams& p, int mblk, int epoch) {
   if (mblk * kBM >= p.rows) return;
@@ -333,12 +227,11 @@ __device__ __forceinline__ bool tile_is_padding(const GemmParams& p, int m0, int
 // rows of A and HALF of the W tile (BN/2 rows), the leader CTA issues tcgen05.mma.cta_group::2 (M = 256) for both, and
 // each CTA's accumulator half lands in its own TMEM.  Shared-memory traffic per MMA cycle drops by 1/4 (BN = 256) —
 // the measured limiter of the single-CTA kernel (operand writes by TMA + reads by the tensor core > 128 B/clk).
-template <int BN, int STAGES, int EPI, int ACT, bool CONV, bool PAIR = false, bool NORMA = false>
+template <int BN, int STAGES, int EPI, int ACT, bool CONV, bool PAIR = false>
 __global__ void __launch_bounds__(gemm_threads(EPI, ACT), 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
   static_assert(!(PAIR && CONV), "the conv schedule is single-CTA");
-  static_assert(!(NORMA && CONV), "fused A normalisation is for plain GEMMs");
   constexpr int BNL = PAIR ? BN / 2 : BN;  // W rows staged by this CTA
   constexpr int TM = PAIR ? 2 * kBM : kBM;  // rows of one (pair-)tile
   constexpr uint32_t A_BYTES = kBM * kBK * 2;
@@ -442,13 +335,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
       }
       if (!linked_in) pdl_wait();
-      const int epoch = ((NORMA || linked_in) && p.step_ptr) ? *p.step_ptr : 0;
+      const int epoch = (linked_in && p.step_ptr) ? *p.step_ptr : 0;
       for (int t = cta_id; t < num_tiles; t += cta_step) {
         const int n0 = (t % tiles_n) * BN;
         const int m0 = ((t / tiles_n) % tiles_m) * TM + int(rank) * kBM;
         const int bz = t / (tiles_n * tiles_m);
         if (tile_is_padding<CONV>(p, ((t / tiles_n) % tiles_m) * TM, TM, bz)) continue;
-        if (NORMA) norm_wait_block(p, m0 / kBM, epoch);  // the epilogue warps of all CTAs are producing this block
         if (linked_in && !tile_is_padding<CONV>(p, m0, kBM, bz)) link_wait_block(p, m0 / kBM, epoch);
         for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
           const int s = it % STAGES;
@@ -521,7 +413,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // Staging buffers: two column groups own one buffer each; a single group (EG = 1) uses BOTH as a ring, so the bulk
     // store of chunk c reads its buffer while chunk c + 1 is already being written into the other one.
     uint32_t cc = 0;                                      // running chunk counter of this group (EG = 1 ring index)
-    if (NORMA) norm_rows_phase(p, int(blockIdx.x) * (ETH / 32) + (et >> 5), int(gridDim.x) * (ETH / 32));
     const float* gate = nullptr;
     if (EPI == EPI_RESID && p.gate != nullptr)
       gate = p.gate + (p.step_ptr ? (long long)(*p.step_ptr) : 0) * p.gate_step_stride;

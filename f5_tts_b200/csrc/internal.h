@@ -50,7 +50,7 @@ struct GemmPlan {
   CUtensorMap tmA, tmB, tmC;
   GemmParams p;
   dim3 grid;
-  int bn, epi, act, conv, pair, norma;
+  int bn, epi, act, conv, pair;
 };
 int gemm_plan(GemmPlan* plan, const void* A, const void* W, const f5_gemm_args* a);
 int gemm_run(const GemmPlan& plan, cudaStream_t s);

@@ -36,15 +36,6 @@ struct GemmParams {
   int conv_pad;  // CONV: taps/2
   int skip_pad;    // 1: 128-row (256 for CTA pairs) tiles whose rows all lie past their sample's row_len are not computed
   int w_prefetch;  // W tiles may be loaded before griddepcontrol.wait (weights are not produced by the predecessor)
-  // NORMA kernels: the A operand is produced by this kernel (row norm + modulation of norm_x), see gemm.cuh
-  const float* norm_x;      // fp32 [rows, norm_d]
-  __half* norm_out;         // fp16 [rows, norm_d] = the buffer tmA points at
-  const float* norm_a;      // mode 0: scale  mode 2: g      (+ step * norm_step_stride)
-  const float* norm_b;      // mode 0: shift
-  long long norm_step_stride;
-  int* norm_ctr;            // [ceil(rows / 128)] rows finished per 128-row block, cumulative over the steps of a sample() call
-  int norm_mode, norm_d;
-  float norm_eps;
   // Block-level hand-off between two GEMMs (gemm.cuh "linked GEMMs"): the producer counts finished tiles per 128-row
   // block of its output, the consumer loads a block of its A operand as soon as that block is complete
   int* done_ctr;         // producer: += 1 per finished (tile, epilogue column group); null = not linked

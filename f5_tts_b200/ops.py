@@ -29,12 +29,11 @@ def _need_cuda(*ts):
 
 
 def linear(a: torch.Tensor, w: torch.Tensor, bias=None, *, epi=EPI_F16, act=ACT_NONE, bn=0, pair=0, resid=None, gate=None,
-           row_len=None, seq=0, rope=None, inner=0, pe_heads=0, out16b=False, static_w=False, norm=None,
+           row_len=None, seq=0, rope=None, inner=0, pe_heads=0, out16b=False, static_w=False,
            done_counters=None, ready=None):
     """C = epilogue(a @ w.T).  a fp16 [M, K], w fp16 [N, K] (both contiguous).
     static_w: w is a model weight (not produced by the preceding kernel) -> its tiles may be prefetched early.
-    norm = (x fp32 [M, K], mode, a, b | None, eps): the kernel computes `a` itself as fp16(norm(x)) (fused AdaLN / RMS
-    normalisation, f5_gemm_args.norm_x); the `a` tensor passed in is then only the scratch buffer."""
+    done_counters / ready = (counters, target): linked GEMMs (f5_gemm_args.done_counters / ready_counters)."""
     _need_cuda(a, w, bias, resid, gate)
     assert a.dtype == torch.float16 and w.dtype == torch.float16 and a.is_contiguous() and w.is_contiguous()
     M, K = a.shape
@@ -70,14 +69,6 @@ def linear(a: torch.Tensor, w: torch.Tensor, bias=None, *, epi=EPI_F16, act=ACT_
         g.done_counters = done_counters.data_ptr()
     if ready is not None:          # ... this call the consumer: (counters, target)
         g.ready_counters, g.ready_target = ready[0].data_ptr(), int(ready[1])
-    keep = None
-    if norm is not None:
-        nx, nmode, na, nb, neps = norm
-        _need_cuda(nx, na, nb)
-        assert nx.dtype == torch.float32 and nx.is_contiguous() and nx.shape == (M, K)
-        keep = torch.zeros((M + 127) // 128, dtype=torch.int32, device=a.device)  # row counters, fresh per call
-        g.norm_x, g.norm_mode, g.norm_a, g.norm_b = nx.data_ptr(), nmode, na.data_ptr(), _ptr(nb)
-        g.norm_step_stride, g.norm_counters, g.norm_eps = 0, keep.data_ptr(), neps
     with torch.cuda.device(a.device):
         _lib.check(_lib.lib().f5_gemm(a.data_ptr(), w.data_ptr(), C.byref(g), _stream(a)), "f5_gemm")
     return (out, out2) if out16b else out

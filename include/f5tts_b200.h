@@ -70,21 +70,6 @@ typedef struct {
   int inner, pe_heads;
   int weights_static;      /* 1 = W was NOT written by the kernel preceding this call on the stream (model weights):
                               its first tiles are fetched ahead of the programmatic-dependent-launch wait */
-  /* Fused A-operand normalisation (AdaLayerNorm / RMSNorm in front of a projection: model/modules.py:312-326,716,
-   * 753-754; unett.py:300-301).  norm_x != NULL: the kernel first computes A[r, :] = fp16(norm(norm_x[r, :])) into the
-   * caller's A buffer (which then is scratch, [rows, k] with lda == k) and multiplies by it — one kernel instead of
-   * f5_row_norm + f5_gemm.  Plain GEMM with batches == 1, k a multiple of 128 and <= 1024, epilogues QKV_ROPE or
-   * F16 + GELU_TANH.  mode 0: LN(eps) * (1 + a[c]) + b[c]; mode 2: x/||x|| * sqrt(k) * a[c]; a, b are indexed with
-   * step_ptr like gate (norm_step_stride elements per step).  norm_counters: ceil(rows / 128) ints, zeroed by the
-   * caller before the first launch; they count finished rows cumulatively, launch n (0-based, *step_ptr) expects
-   * rows x (n + 1). */
-  const float* norm_x;
-  int norm_mode;
-  const float* norm_a;
-  const float* norm_b;
-  long long norm_step_stride;
-  int* norm_counters;
-  float norm_eps;
   /* Packed / variable-length execution: 1 = output tiles whose rows all lie past row_len of their sample are skipped
    * entirely (not loaded, multiplied or stored: their output rows keep whatever the buffer held).  Needs row_len and
    * seq.  The reference's counterpart is its masked mode (flash_attn_varlen / attn_mask, modules.py:513-540). */
@@ -93,7 +78,8 @@ typedef struct {
    * e.g. ff.ff[0] -> ff.ff[2], modules.py:360-361): the producer call passes done_counters (ceil(rows / 128) ints, zeroed
    * before the first launch), the consumer call passes the same array as ready_counters plus ready_target =
    * f5_gemm_link_target(producer args).  The consumer then starts on a 128-row block as soon as the producer has
-   * finished it instead of waiting for the producer's whole grid.  Counters are cumulative like norm_counters. */
+   * finished it instead of waiting for the producer's whole grid.  Counters are cumulative over launches: launch n (0-based, *step_ptr)
+   * expects ready_target x (n + 1). */
   int* done_counters;
   const int* ready_counters;
   int ready_target;

@@ -231,42 +231,6 @@ def test_vocos_decode(golden_dir):
 
 
 
-@pytest.mark.parametrize("M,bn,pair", [(1876, 0, 0), (1876, 128, 0), (300, 192, 0), (4000, 256, 1), (129, 256, 0), (15008, 0, 0)])
-@pytest.mark.parametrize("mode", [0, 2])
-def test_gemm_fused_row_norm(M, bn, pair, mode):
-    """NORMA kernels (f5_gemm_args.norm_x): the GEMM normalises its own A operand — AdaLN LayerNorm * (1 + scale) + shift
-    (modules.py:312-326) or x_transformers RMSNorm (unett.py:154) — then multiplies.  Must equal f5_row_norm + f5_gemm
-    bit for bit (same arithmetic, same fp16 rounding of A), and the fp32 reference within the fp16-output tolerance."""
-    D, N = 1024, 2048
-    x = gen((M, D), 51, 1.0, torch.float32) * 3 + 0.5
-    sc, sh = gen((D,), 52, 0.3, torch.float32), gen((D,), 53, 0.3, torch.float32)
-    w = gen((N, D), 54, 1 / math.sqrt(D))
-    bias = gen((N,), 55, 0.5, torch.float32)
-    scratch = torch.empty((M, D), dtype=torch.float16, device=DEV)
-    got = ops.linear(scratch, w, bias, epi=EPI_F16, act=ACT_GELU_TANH, bn=bn, pair=pair,
-                     norm=(x, mode, sc, sh if mode == 0 else None, 1e-6))
-    a_sep = ops.row_norm(x, mode, sc, sh if mode == 0 else None)
-    sep = ops.linear(a_sep, w, bias, epi=EPI_F16, act=ACT_GELU_TANH, bn=bn, pair=pair)
-    assert torch.equal(scratch, a_sep), "the fused normalisation writes the same fp16 A operand as f5_row_norm"
-    assert torch.equal(got, sep)
-    if mode == 0:
-        a_ref = F.layer_norm(x, (D,), eps=1e-6) * (1 + sc) + sh
-    else:
-        a_ref = F.normalize(x, dim=-1) * math.sqrt(D) * sc
-    ref = F.gelu(a_ref.half().float() @ w.float().t() + bias, approximate="tanh")
-    report(f"fused norm gemm M={M} bn={bn} pair={pair} mode={mode}", got, ref)
-    assert rel(got, ref) <= 1.5e-3
-    # QKV + RoPE epilogue variant
-    seq = M
-    cs, sn = ops.rope_tables(seq, DEV)
-    w3 = gen((3 * D, D), 56, 1 / math.sqrt(D))
-    b3 = gen((3 * D,), 57, 0.5, torch.float32)
-    g1 = ops.linear(scratch, w3, b3, epi=EPI_QKV_ROPE, bn=bn, pair=pair, seq=seq, rope=(cs, sn), inner=D, pe_heads=1,
-                    norm=(x, mode, sc, sh if mode == 0 else None, 1e-6))
-    g2 = ops.linear(a_sep, w3, b3, epi=EPI_QKV_ROPE, bn=bn, pair=pair, seq=seq, rope=(cs, sn), inner=D, pe_heads=1)
-    assert torch.equal(g1, g2)
-
-
 @pytest.mark.parametrize("M", [1876, 500, 15008])
 def test_gemm_linked_ff1_ff2(M):
     """Linked GEMMs (f5_gemm_args.done_counters / ready_counters): FF2 consumes FF1's output block by block instead of
