@@ -134,7 +134,7 @@ def build_gpu_model(arch_name, dev):
     return model.to(dev), voc.to(dev), cfg
 
 
-def hot_path(model, voc, wav, text, duration, lens, nfe, frames0=None):
+def hot_path(model, voc, wav, text, duration, lens, nfe, frames0=None, exact_varlen=False):
     """mel front-end + CFM.sample + vocoder; returns (mel [B,N,100], audio [B, nw])."""
     B = wav.shape[0]
     if B == 1:
@@ -144,7 +144,7 @@ def hot_path(model, voc, wav, text, duration, lens, nfe, frames0=None):
     else:
         cond = model.mel_spec(wav, frames_last=False)
         out, _ = model.sample(cond, text, duration, lens=lens, steps=nfe, cfg_strength=CFG_STRENGTH,
-                              sway_sampling_coef=SWAY, seed=0)
+                              sway_sampling_coef=SWAY, seed=0, exact_varlen=exact_varlen)
         ref = int(lens.min())
     audio = voc.decode(out[:, ref:, :].permute(0, 2, 1).float())
     return out, audio
@@ -432,6 +432,43 @@ def extra_workloads(dev, world, rank, dist, barrier, models):
                              rtf=round(ms * 1e-3 / (gen * 256 / 24000.0), 5), steps=3, warmup=2,
                              step_tflops=round(flops / (ms * 1e-3) / 1e12, 1),
                              mode="faithful (padded rows computed and attended, as the reference's batched call)"))
+        # cfg3 again in packed / variable-length execution: every utterance exactly as if alone in the
+        # batch — keys masked, padded tiles skipped (the reference's counterpart is its masked / varlen mode)
+        w = WORKLOADS["cfg3"]
+        model, voc = models(w["arch"])
+        wav, text, duration, lens = (t.to(dev) for t in synth_inputs(w))
+        ms = timed(lambda: hot_path(model, voc, wav, text, duration, lens, w["nfe"], exact_varlen=True), 3, 2, barrier)
+        gen = sum(f - r for f, r in zip(w["frames"], w["ref"]))
+        recs.append(dict(workload="cfg3", arch=w["arch"], batch=w["B"], frames=w["frames"], nfe=w["nfe"], n_gpus=1,
+                         ms_per_step=round(ms, 2), value=round(gen / (ms * 1e-3), 1), unit="mel_frames/s",
+                         rtf=round(ms * 1e-3 / (gen * 256 / 24000.0), 5), steps=3, warmup=2,
+                         mode="exact_varlen (keys masked per utterance, tiles that hold only padding skipped)"))
+        # one request of several text chunks through infer_batch_process: ONE batched sampler call (exact_varlen, shared
+        # prompt mel, device-side cross-fade) against the reference's structure, one sampler call per chunk
+        from f5_tts_b200 import infer as INF
+
+        w2 = WORKLOADS["cfg2"]
+        model, voc = models(w2["arch"])
+        audio_h = synth_inputs(w2)[0].clone().pin_memory()
+        ref_text = "some call me nature others call me mother na."
+        base = "i have been a silent spectator watching species evolve and empires rise and fall but always remember i am mighty"
+        chunks = [base[:100] + ".", base[:70] + ".", base[:90] + ".", base[:60] + "."]
+        kw = dict(nfe_step=w2["nfe"], cfg_strength=CFG_STRENGTH, sway_sampling_coef=SWAY, device=dev)
+
+        def batched():
+            return next(INF.infer_batch_process((audio_h, 24000), ref_text, chunks, model, voc, **kw))
+
+        def per_chunk():
+            return [next(INF.infer_batch_process((audio_h, 24000), ref_text, [c], model, voc, **kw)) for c in chunks]
+
+        frames = batched()[2].shape[-1]
+        ms_b = timed(batched, 3, 1, barrier)
+        ms_s = timed(per_chunk, 3, 1, barrier)
+        recs.append(dict(workload="chunked request (4 text chunks, 10 s prompt-conditioned each, NFE 32) through infer_batch_process",
+                         generated_frames=int(frames), n_gpus=1, steps=3, warmup=1,
+                         batched_ms=round(ms_b, 2), per_chunk_ms=round(ms_s, 2), speedup=round(ms_s / ms_b, 3),
+                         value=round(frames / (ms_b * 1e-3), 1), unit="mel_frames/s",
+                         note="host audio in, host waveform out; batched = one exact_varlen sampler call for all chunks"))
     # cfg4: 64 fixed 10 s utterances, NFE 16, sharded by utterance over the ranks; batches of 8 per sampler call
     w = WORKLOADS["cfg4"]
     model, voc = models(w["arch"])

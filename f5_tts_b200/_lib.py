@@ -28,7 +28,6 @@ class GemmArgs(C.Structure):
         ("seq", c_int), ("rope_cos", c_void_p), ("rope_sin", c_void_p), ("inner", c_int), ("pe_heads", c_int),
         ("weights_static", c_int),
         ("skip_padded_tiles", c_int),
-        ("done_counters", c_void_p), ("ready_counters", c_void_p), ("ready_target", c_int),
     ]
 
 
@@ -104,8 +103,6 @@ def lib():
         L.f5_launch_count.restype = C.c_ulonglong
         L.f5_gemm.argtypes = [c_void_p, c_void_p, C.POINTER(GemmArgs), c_void_p]
         L.f5_gemm_tile.argtypes = [C.POINTER(GemmArgs), C.POINTER(c_int), C.POINTER(c_int)]
-        L.f5_gemm_link_target.argtypes = [C.POINTER(GemmArgs)]
-        L.f5_gemm_link_target.restype = c_int
         L.f5_attention.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_float, c_void_p]
         L.f5_row_norm.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p]
         L.f5_mel_spectrogram.argtypes = [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p]
@@ -121,7 +118,7 @@ def lib():
         L.f5_sample.argtypes = [c_void_p, C.POINTER(SampleArgs), c_void_p, c_size_t, c_void_p]
         L.f5_sample_flops.argtypes = [c_void_p, c_int, c_int, c_int, c_float]
         L.f5_sample_flops.restype = C.c_double
-        for name in ("f5_gemm", "f5_gemm_tile", "f5_gemm_link_target", "f5_attention", "f5_row_norm", "f5_mel_spectrogram", "f5_vocos_decode",
+        for name in ("f5_gemm", "f5_gemm_tile", "f5_attention", "f5_row_norm", "f5_mel_spectrogram", "f5_vocos_decode",
                      "f5_engine_create", "f5_sample"):
             getattr(L, name).restype = c_int
         _lib = L
@@ -139,7 +136,7 @@ def launch_count() -> int:
 
 
 EXPORTED_SYMBOLS = [
-    "f5_version", "f5_last_error", "f5_launch_count", "f5_debug_gemm_trace", "f5_debug_attn_trace", "f5_gemm", "f5_gemm_tile", "f5_gemm_link_target", "f5_attention", "f5_row_norm", "f5_mel_spectrogram",
+    "f5_version", "f5_last_error", "f5_launch_count", "f5_debug_gemm_trace", "f5_debug_attn_trace", "f5_gemm", "f5_gemm_tile", "f5_attention", "f5_row_norm", "f5_mel_spectrogram",
     "f5_vocos_workspace_bytes", "f5_vocos_decode", "f5_engine_create", "f5_engine_destroy",
     "f5_sample_workspace_bytes", "f5_sample", "f5_sample_flops",
 ]

@@ -104,34 +104,27 @@ constexpr int kPolyOf8 = 3;  // element pairs (of every 8) whose 2^x runs on the
 // POLY = pairs of every 8 computed with the polynomial (evenly interleaved with the MUFU ones).
 template <int POLY>
 __device__ __forceinline__ void exp_pack32(const uint32_t (&r)[32], int col0, int kv_rem, uint64_t sc2, uint64_t nms2,
-                                           uint64_t& sum2, uint32_t (&pk)[16]) {
+                                           uint64_t& sum2, uint32_t* pk) {
   if (col0 >= kv_rem) {  // warp-uniform: every key of this chunk is past the end of the sample -> P = 0
 #pragma unroll
     for (int i = 0; i < 16; ++i) pk[i] = 0u;
     return;
   }
-  // three passes over the 16 pairs (arguments, exponentials, sums + packing): the exponentials of all pairs are in
-  // flight before the first consumer needs one, so the in-order issue does not stall on each MUFU result in turn
-  uint64_t x2[16];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) x2[i] = f2_fma(f2_pack(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), sc2, nms2);
-  float e[32];
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
+    const uint64_t x2 = f2_fma(f2_pack(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), sc2, nms2);
+    float e0, e1;
     const int pi = i & 7;
     if (((pi + 1) * POLY) / 8 != (pi * POLY) / 8) {  // compile-time pattern
-      ex2_poly2(x2[i], e[2 * i], e[2 * i + 1]);
+      ex2_poly2(x2, e0, e1);
     } else {
       float x0, x1;
-      f2_unpack(x2[i], x0, x1);
-      e[2 * i] = ex2_approx(x0);
-      e[2 * i + 1] = ex2_approx(x1);
+      f2_unpack(x2, x0, x1);
+      e0 = ex2_approx(x0);
+      e1 = ex2_approx(x1);
     }
-  }
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    sum2 = f2_add(sum2, f2_pack(e[2 * i], e[2 * i + 1]));
-    pk[i] = pack_half2(e[2 * i], e[2 * i + 1]);
+    sum2 = f2_add(sum2, f2_pack(e0, e1));
+    pk[i] = pack_half2(e0, e1);
   }
 }
 
@@ -346,37 +339,11 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnPar
       const uint64_t sc2 = f2_pack(p.scale_log2, p.scale_log2);
       const uint64_t nms2 = f2_pack(-m_run, -m_run);
       uint64_t sum2 = f2_pack(0.0f, 0.0f);
-      // The P columns (and O) are free once the previous tile's P V has retired — long before this point in steady state
-      // (it was issued right after the previous P was published).  Waiting here, BEFORE the exponentials, lets every
-      // 32-key chunk of P go to TMEM as soon as it is packed: 16 packed registers are live at a time instead of 64, which
-      // leaves the scheduler room to keep the MUFU pipe fed (with 192 values live, each result was consumed in turn).
-      if (j > 0) {
-        mbar_wait(&o_full[w], (j - 1) & 1);
-        tc_fence_after();
-      }
-#ifdef F5_TRACE
-      if (ts) { const long long c1 = clock64(); c_o += c1 - c0; c0 = c1; }
-#endif
-      {
-        uint32_t pk[16];
-        exp_pack32<POLY>(r0, 0, kv_rem, sc2, nms2, sum2, pk);
-        tmem_st16(tmem_P, pk);
-      }
-      {
-        uint32_t pk[16];
-        exp_pack32<POLY>(r1, 32, kv_rem, sc2, nms2, sum2, pk);
-        tmem_st16(tmem_P + 16, pk);
-      }
-      {
-        uint32_t pk[16];
-        exp_pack32<POLY>(r2, 64, kv_rem, sc2, nms2, sum2, pk);
-        tmem_st16(tmem_P + 32, pk);
-      }
-      {
-        uint32_t pk[16];
-        exp_pack32<POLY>(r3, 96, kv_rem, sc2, nms2, sum2, pk);
-        tmem_st16(tmem_P + 48, pk);
-      }
+      uint32_t pa[32], pb[32];  // keys 0..63 / 64..127 as fp16 pairs = TMEM columns 0..31 / 32..63 of P_w
+      exp_pack32<POLY>(r0, 0, kv_rem, sc2, nms2, sum2, pa);
+      exp_pack32<POLY>(r1, 32, kv_rem, sc2, nms2, sum2, pa + 16);
+      exp_pack32<POLY>(r2, 64, kv_rem, sc2, nms2, sum2, pb);
+      exp_pack32<POLY>(r3, 96, kv_rem, sc2, nms2, sum2, pb + 16);
       float ls0, ls1;
       f2_unpack(sum2, ls0, ls1);
       l_run = l_run * alpha + (ls0 + ls1);
@@ -384,6 +351,16 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnPar
 #ifdef F5_TRACE
       if (ts) { const long long c1 = clock64(); c_exp += c1 - c0; c0 = c1; }
 #endif
+      if (j > 0) {
+        mbar_wait(&o_full[w], (j - 1) & 1);  // P V of the previous tile retired: the P columns and O are ours
+        tc_fence_after();
+      }
+#ifdef F5_TRACE
+      if (ts) { const long long c1 = clock64(); c_o += c1 - c0; c0 = c1; }
+#endif
+      // P -> TMEM (A operand of the P V product): lane = query row, column c holds keys 2c, 2c + 1
+      tmem_st32(tmem_P, pa);
+      tmem_st32(tmem_P + 32, pb);
       if (do_rescale && j > 0) {
 #pragma unroll 1
         for (int c = 0; c < 2; ++c) {

@@ -42,8 +42,6 @@ struct Layout {
   // common
   int* step_ptr;
   SampleIo* io;     // caller tensors + cfg scale of THIS call, read by the step kernels through the workspace
-  int* link_ctr;    // [depth][ceil(M1 / 128)] tile counters of the FF1 -> FF2 hand-off (gemm.cuh: linked GEMMs)
-  int norm_blocks;  // ceil(M1 / 128)
   float* dt;
   float* t_dev;
   float *rope_cos, *rope_sin;
@@ -122,8 +120,6 @@ static void plan_layout(const f5_engine* e, Layout& L, void* ws, int B, int N, i
   const int D = A.dim, Td = A.text_dim, F = A.ff_inner;
   L.step_ptr = bp.take<int>(64);
   L.io = bp.take<SampleIo>(1);
-  L.norm_blocks = (int)((L.M1 + 127) / 128);
-  L.link_ctr = bp.take<int>((size_t)A.depth * L.norm_blocks);
   L.dt = bp.take<float>(steps + 1);
   L.t_dev = bp.take<float>(steps + 1);
   L.rope_cos = bp.take<float>((size_t)L.seq * 32);
@@ -335,7 +331,6 @@ int build_step_plans(f5_engine* e, const Layout& L, const f5_sample_args* sa, St
     a.seq = L.seq;
     a.skip_padded_tiles = 1;
   };
-  int ff1_link_target = 0;
   for (int i = 0; i < A.depth; ++i) {
     const f5_layer_weights& lw = W.layers[i];
     if (!dit && lw.w_skip) {
@@ -378,10 +373,6 @@ int build_step_plans(f5_engine* e, const Layout& L, const f5_sample_args* sa, St
       a.out = L.g;
       a.ldo = F;
       varlen(a);
-#ifndef F5_NO_LINK
-      a.done_counters = L.link_ctr + (size_t)i * L.norm_blocks;  // FF2 starts block by block (linked GEMMs)
-      ff1_link_target = f5_gemm_link_target(&a);
-#endif
       RC(gemm_plan(&P.ff1[i], L.a, lw.w_ff1, &a));
     }
     {
@@ -395,11 +386,6 @@ int build_step_plans(f5_engine* e, const Layout& L, const f5_sample_args* sa, St
         a.gate_step_stride = modS;
       }
       varlen(a);
-#ifndef F5_NO_LINK
-      a.ready_counters = L.link_ctr + (size_t)i * L.norm_blocks;
-      a.ready_target = ff1_link_target;
-      a.step_ptr = L.step_ptr;
-#endif
       RC(gemm_plan(&P.ff2[i], L.g, lw.w_ff2, &a));
     }
   }
@@ -519,7 +505,6 @@ int run_prologue(f5_engine* e, const Layout& L, const f5_sample_args* sa, cudaSt
   RC(check_cuda(cudaMemcpyAsync(L.dt, dt.data(), sizeof(float) * (S + 1), cudaMemcpyHostToDevice, s), "dt h2d"));
   RC(check_cuda(cudaMemcpyAsync(L.t_dev, sa->t, sizeof(float) * (S + 1), cudaMemcpyHostToDevice, s), "t h2d"));
   RC(check_cuda(cudaMemsetAsync(L.step_ptr, 0, sizeof(int) * 64, s), "step memset"));
-  RC(check_cuda(cudaMemsetAsync(L.link_ctr, 0, sizeof(int) * A.depth * L.norm_blocks, s), "block counters"));
   SampleIo io{sa->y, sa->trajectory, sa->cfg_strength};
   RC(check_cuda(cudaMemcpyAsync(L.io, &io, sizeof(io), cudaMemcpyHostToDevice, s), "io h2d"));
   if (masked) {

@@ -335,27 +335,6 @@ int gemm_plan(GemmPlan* pl, const void* A, const void* W, const f5_gemm_args* a)
   p.skip_pad = (a->skip_padded_tiles && a->row_len != nullptr && a->seq > 0 && (conv || a->batches == 1)) ? 1 : 0;
   // a prefetched W tile belongs to the CTA's first tile: not known to be computed when padded tiles are skipped
   p.w_prefetch = (a->weights_static && !p.skip_pad) ? 1 : 0;
-  p.done_ctr = (a->epi != F5_EPI_F32 && !conv) ? a->done_counters : nullptr;  // staged epilogues only
-  p.ready_ctr = !conv && a->batches == 1 ? a->ready_counters : nullptr;
-  p.ready_target = a->ready_target;
-#ifdef F5_TRACE  // instrumented build only: kernel skip modes (wrong results) and the per-CTA timestamp trace
-  {
-    static int dbg = -1;
-    if (dbg < 0) {
-      const char* e = getenv("F5_GEMM_DBG");
-      dbg = e ? atoi(e) : 0;
-    }
-    p.dbg_mode = dbg;
-    static long long* trace = nullptr;
-    static int want_trace = -1;
-    if (want_trace < 0) {
-      want_trace = getenv("F5_GEMM_TRACE") ? 1 : 0;
-      if (want_trace) cudaMalloc(&trace, sizeof(long long) * 16 * 1024);
-    }
-    p.dbg_ts = trace;
-    g_trace = trace;
-  }
-#endif
   int rc;
   if (conv) {
     if (a->n_out % 64 || a->lda < a->n_out) {
@@ -439,13 +418,6 @@ int f5_gemm_tile(const f5_gemm_args* args, int* bn, int* cta_pair) {
   *bn = b;
   *cta_pair = (args->conv_taps == 0 && pr && args->epi != F5_EPI_F32 && b >= 128) ? 1 : 0;
   return 0;
-}
-
-int f5_gemm_link_target(const f5_gemm_args* args) {
-  if (!args) return -1;
-  int bn = 0, pair = 0;
-  if (f5_gemm_tile(args, &bn, &pair)) return -1;
-  return ((args->n_out + bn - 1) / bn) * f5::gemm_epi_groups(args->epi, args->act);
 }
 
 int f5_gemm(const void* A, const void* W, const f5_gemm_args* args, f5_stream_t stream) {

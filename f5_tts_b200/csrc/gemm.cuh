@@ -41,11 +41,7 @@ constexpr int kEpiBufs = 2;                     // one staging buffer per epilog
 // ~2x the instructions) get a second column group (measured FF1: 14.1 -> 12.4 us at M = 1876, 1025 -> 1196 TFLOP/s at
 // M = 15008); the plain / RoPE / reduce-add epilogues were not faster with eight warps (register cap 168, single TMEM
 // buffer) and keep four.
-#ifdef F5_RESID_EG2  // experiment build: fp32 reduce-add epilogues on two column groups as well (tools/gemm_sweep.py A/B)
-__host__ __device__ constexpr int gemm_epi_groups(int epi, int act) { return (act != ACT_NONE || epi == EPI_RESID) ? 2 : 1; }
-#else
 __host__ __device__ constexpr int gemm_epi_groups(int /*epi*/, int act) { return act != ACT_NONE ? 2 : 1; }
-#endif
 __host__ __device__ constexpr int gemm_threads(int epi, int act) { return 64 + 128 * gemm_epi_groups(epi, act); }
 
 template <int BN, int STAGES, bool PAIR = false>
@@ -175,40 +171,6 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
   }
 }
 
-// TMA producer side: spin (acquire) until counter `c` has reached `target`, then order the async-proxy reads after it
-__device__ __forceinline__ void wait_counter(const int* c, int target, int mblk);
-
-// ---- linked GEMMs ---------------------------------------------------------------------------------------------------
-// FF1 (240 tiles at cfg2) runs 1.6 rounds over 148 SMs: in its second round 56 SMs are idle, and FF2 (120 tiles, one
-// round) could not start before the whole FF1 grid had drained.  Linked, the producer GEMM publishes one counter per
-// 128-row block of its output (+1 per finished tile and epilogue column group, after the bulk stores of the tile have
-// completed), and the consumer — launched programmatically early, it never executes griddepcontrol.wait — loads a block
-// of its A operand as soon as that block's counter says all of the producer's column tiles are in memory.  Its CTAs
-// take over the SMs the producer's one-tile CTAs vacate and work on the blocks the producer's first round finished.
-// Safe without the grid-wide wait: everything else the consumer reads (weights, bias, gate row, step counter) predates
-// the producer, and the residual rows it reduce-adds into were last READ by the row-norm kernel in front of the
-// producer, which the producer itself waited for.  No deadlock: the consumer can only be scheduled
-// after every producer CTA is resident (programmatic launch), and the producer is a persistent grid.
-__device__ __forceinline__ void link_wait_block(const GemmParams& p, int mblk, int epoch) {
-  if (mblk * kBM >= p.rows) return;
-  wait_counter(p.ready_ctr + mblk, p.ready_target * (epoch + 1), mblk);
-}
-
-__device__ __forceinline__ void wait_counter(const int* c, int target, int mblk) {
-  int v;
-  long long t0 = 0;
-  for (;;) {
-    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(c) : "memory");
-    if (v >= target) break;
-    if (t0 == 0) t0 = clock64();
-    if (clock64() - t0 > F5_SPIN_TIMEOUT_CYCLES) {
-      printf("f5: block counter wait timeout block %d mblk %d have %d want %d\n", blockIdx.x, mblk, v, target);
-      __trap();
-    }
-  }
-  asm volatile("fence.proxy.async.global;" ::: "memory");
-}
-
 // Packed / variable-length execution (reference masked mode modules.py:513-540): with skip_pad, a tile
 // whose rows ALL lie past the end of their sample is never loaded, multiplied or stored.  Every warp role evaluates the
 // same predicate, so the smem ring, the TMEM double buffer and the tile order stay in step.  m0 = first row of the
@@ -299,9 +261,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   // Programmatic dependent launch: everything above overlapped the predecessor's tail.  The producer thread goes one
   // step further (below): W tiles are weights, not produced by the predecessor, so their TMA loads are issued BEFORE
   // the dependency wait and the DRAM latency of the first STAGES k-blocks hides under the predecessor too.
-  // linked consumer (ready_ctr): no grid-wide wait at all — its A operand arrives block by block (link_wait_block)
-  const bool linked_in = p.ready_ctr != nullptr;
-  if (warp != 0 && !linked_in) pdl_wait();  // predecessor kernel finished: its outputs (A operand, residual, ...) are visible
+  if (warp != 0) pdl_wait();  // predecessor kernel finished: its outputs (our A operand, residual, ...) are visible
   pdl_launch_dependents();    // let the next kernel's prologue overlap our tail
 #ifdef F5_TRACE
   if (ts && threadIdx.x == 0) ts[2] = clock64();  // setup done
@@ -334,14 +294,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           load_w(int(kb), int(kb), (cta_id % tiles_n) * BN);
         }
       }
-      if (!linked_in) pdl_wait();
-      const int epoch = (linked_in && p.step_ptr) ? *p.step_ptr : 0;
+      pdl_wait();
       for (int t = cta_id; t < num_tiles; t += cta_step) {
         const int n0 = (t % tiles_n) * BN;
         const int m0 = ((t / tiles_n) % tiles_m) * TM + int(rank) * kBM;
         const int bz = t / (tiles_n * tiles_m);
         if (tile_is_padding<CONV>(p, ((t / tiles_n) % tiles_m) * TM, TM, bz)) continue;
-        if (linked_in && !tile_is_padding<CONV>(p, m0, kBM, bz)) link_wait_block(p, m0 / kBM, epoch);
         for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
@@ -583,13 +541,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               tma_store_commit();
             }
           }
-        }
-        if (p.done_ctr != nullptr && issuer && m0 < p.rows) {
-          // linked producer: this group's bulk stores of the tile are complete (not merely read out of shared memory)
-          tma_store_wait_all();
-          asm volatile("fence.proxy.async.global;" ::: "memory");
-          __threadfence();
-          atomicAdd(p.done_ctr + m0 / kBM, 1);
         }
       }
       tc_fence_before();

@@ -36,11 +36,6 @@ struct GemmParams {
   int conv_pad;  // CONV: taps/2
   int skip_pad;    // 1: 128-row (256 for CTA pairs) tiles whose rows all lie past their sample's row_len are not computed
   int w_prefetch;  // W tiles may be loaded before griddepcontrol.wait (weights are not produced by the predecessor)
-  // Block-level hand-off between two GEMMs (gemm.cuh "linked GEMMs"): the producer counts finished tiles per 128-row
-  // block of its output, the consumer loads a block of its A operand as soon as that block is complete
-  int* done_ctr;         // producer: += 1 per finished (tile, epilogue column group); null = not linked
-  const int* ready_ctr;  // consumer: rows of block b may be loaded once ready_ctr[b] >= ready_target * (step + 1)
-  int ready_target;
   long long* dbg_ts;  // optional [gridDim.x][8] clock64/globaltimer trace (diagnostics; NULL in production)
   int dbg_mode;  // 0 normal; 1 = skip TMA loads, 2 = skip MMAs, 3 = skip epilogue math/stores (perf decomposition only)
 };

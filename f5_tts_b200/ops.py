@@ -29,11 +29,10 @@ def _need_cuda(*ts):
 
 
 def linear(a: torch.Tensor, w: torch.Tensor, bias=None, *, epi=EPI_F16, act=ACT_NONE, bn=0, pair=0, resid=None, gate=None,
-           row_len=None, seq=0, rope=None, inner=0, pe_heads=0, out16b=False, static_w=False,
-           done_counters=None, ready=None):
+           row_len=None, seq=0, rope=None, inner=0, pe_heads=0, out16b=False, static_w=False):
     """C = epilogue(a @ w.T).  a fp16 [M, K], w fp16 [N, K] (both contiguous).
     static_w: w is a model weight (not produced by the preceding kernel) -> its tiles may be prefetched early.
-    done_counters / ready = (counters, target): linked GEMMs (f5_gemm_args.done_counters / ready_counters)."""
+"""
     _need_cuda(a, w, bias, resid, gate)
     assert a.dtype == torch.float16 and w.dtype == torch.float16 and a.is_contiguous() and w.is_contiguous()
     M, K = a.shape
@@ -65,20 +64,9 @@ def linear(a: torch.Tensor, w: torch.Tensor, bias=None, *, epi=EPI_F16, act=ACT_
         g.rope_cos, g.rope_sin = rope[0].data_ptr(), rope[1].data_ptr()
     g.inner, g.pe_heads = inner, pe_heads
     g.weights_static = 1 if static_w else 0
-    if done_counters is not None:  # linked GEMMs: this call is the producer
-        g.done_counters = done_counters.data_ptr()
-    if ready is not None:          # ... this call the consumer: (counters, target)
-        g.ready_counters, g.ready_target = ready[0].data_ptr(), int(ready[1])
     with torch.cuda.device(a.device):
         _lib.check(_lib.lib().f5_gemm(a.data_ptr(), w.data_ptr(), C.byref(g), _stream(a)), "f5_gemm")
     return (out, out2) if out16b else out
-
-
-def gemm_link_target(M: int, N: int, K: int, epi=EPI_F16, act=ACT_NONE, bn=0, pair=0) -> int:
-    """Counter increments per 128-row block and launch of a producer GEMM of this shape (f5_gemm_link_target)."""
-    g = _lib.GemmArgs()
-    g.rows, g.batches, g.n_out, g.k, g.bn, g.epi, g.act, g.cta_pair = M, 1, N, K, bn, epi, act, pair
-    return int(_lib.lib().f5_gemm_link_target(C.byref(g)))
 
 
 def gemm_tile(M: int, N: int, K: int, epi=EPI_F16, act=ACT_NONE, bn=0, pair=0):

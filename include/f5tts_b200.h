@@ -74,18 +74,7 @@ typedef struct {
    * entirely (not loaded, multiplied or stored: their output rows keep whatever the buffer held).  Needs row_len and
    * seq.  The reference's counterpart is its masked mode (flash_attn_varlen / attn_mask, modules.py:513-540). */
   int skip_padded_tiles;
-  /* Linked GEMMs (two consecutive f5_gemm calls on one stream, the second consuming the first's output as its A operand,
-   * e.g. ff.ff[0] -> ff.ff[2], modules.py:360-361): the producer call passes done_counters (ceil(rows / 128) ints, zeroed
-   * before the first launch), the consumer call passes the same array as ready_counters plus ready_target =
-   * f5_gemm_link_target(producer args).  The consumer then starts on a 128-row block as soon as the producer has
-   * finished it instead of waiting for the producer's whole grid.  Counters are cumulative over launches: launch n (0-based, *step_ptr)
-   * expects ready_target x (n + 1). */
-  int* done_counters;
-  const int* ready_counters;
-  int ready_target;
 } f5_gemm_args;
-/* Increments the producer described by `args` adds to a block counter per launch: column tiles x epilogue groups. */
-int f5_gemm_link_target(const f5_gemm_args* args);
 int f5_gemm(const void* A, const void* W, const f5_gemm_args* args, f5_stream_t stream);
 /* Tile shape f5_gemm would run `args` with (after bn = 0 resolution): *bn tile width, *cta_pair 0/1. */
 int f5_gemm_tile(const f5_gemm_args* args, int* bn, int* cta_pair);

@@ -228,30 +228,3 @@ def test_vocos_decode(golden_dir):
     mel2 = (torch.randn(2, 100, 33, generator=g) * 1.5 - 2.0)
     ref2 = O.vocos_decode(O.synthetic_vocos_state_dict(), mel2)
     assert rel(voc.decode(mel2.to(DEV)).cpu(), ref2) <= 1e-2
-
-
-
-@pytest.mark.parametrize("M", [1876, 500, 15008])
-def test_gemm_linked_ff1_ff2(M):
-    """Linked GEMMs (f5_gemm_args.done_counters / ready_counters): FF2 consumes FF1's output block by block instead of
-    waiting for FF1's whole grid.  Same arithmetic, so the residual must equal the unlinked pair bit for bit; repeated
-    (cumulative counters, as inside a replayed step graph) with the step counter advancing."""
-    D, Fd = 1024, 2048
-    a = gen((M, D), 61)
-    w1, b1 = gen((Fd, D), 62, 1 / math.sqrt(D)), gen((Fd,), 63, 0.5, torch.float32)
-    w2, b2 = gen((D, Fd), 64, 1 / math.sqrt(Fd)), gen((D,), 65, 0.5, torch.float32)
-    gate = gen((D,), 66, 0.5, torch.float32)
-    x0 = gen((M, D), 67, 1.0, torch.float32)
-    g_ref = ops.linear(a, w1, b1, epi=EPI_F16, act=ACT_GELU_TANH)
-    x_ref = x0.clone()
-    ops.linear(g_ref, w2, b2, epi=EPI_RESID, resid=x_ref, gate=gate)
-    ctr = torch.zeros((M + 127) // 128, dtype=torch.int32, device=DEV)
-    target = ops.gemm_link_target(M, Fd, D, EPI_F16, ACT_GELU_TANH)
-    assert target > 0
-    x = x0.clone()
-    g = ops.linear(a, w1, b1, epi=EPI_F16, act=ACT_GELU_TANH, done_counters=ctr)
-    # the consumer reads `g` (the tensor the producer call returned) on the same stream, right behind the producer
-    ops.linear(g, w2, b2, epi=EPI_RESID, resid=x, gate=gate, ready=(ctr, target))
-    torch.cuda.synchronize()
-    assert torch.equal(g, g_ref) and torch.equal(x, x_ref)
-    assert ctr.tolist() == [target] * ctr.numel()
