@@ -320,9 +320,32 @@ __global__ void small_linear_kernel(const float* in, const __half* W, const floa
   const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (n >= Nout) return;
   const int lane = lane_id();
+  const __half* wrow = W + (long long)n * K;
+  if (K <= 1024 && (K & 31) == 0) {
+    // the weight row is read ONCE into registers (lane l holds k = l, l + 32, ...) and reused for all S input rows —
+    // the loop below keeps the accumulation order of the generic path (k ascending per lane, then the warp tree)
+    float w[32];
+    const int nk = K >> 5;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) w[i] = i < nk ? __half2float(wrow[lane + 32 * i]) : 0.f;
+    const float bv = bias ? bias[n] : 0.f;
+    for (int s = 0; s < S; ++s) {
+      const float* x = in + (long long)s * K + lane;
+      float acc = 0.f;
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (i < nk) acc += x[32 * i] * w[i];
+      acc = warp_sum(acc);
+      if (lane == 0) {
+        acc += bv;
+        out[(long long)s * Nout + n] = ACT == 1 ? silu(acc) : acc;
+      }
+    }
+    return;
+  }
   for (int s = 0; s < S; ++s) {
     float acc = 0.f;
-    for (int k = lane; k < K; k += 32) acc += in[(long long)s * K + k] * __half2float(W[(long long)n * K + k]);
+    for (int k = lane; k < K; k += 32) acc += in[(long long)s * K + k] * __half2float(wrow[k]);
     acc = warp_sum(acc);
     if (lane == 0) {
       acc += bias ? bias[n] : 0.f;

@@ -175,6 +175,34 @@ def test_attention(Be, seq, H, kv):
     assert rel(out, ref) <= 3e-3
 
 
+@pytest.mark.parametrize("mode", ["wide", "rising", "falling", "spike"])
+def test_attention_reference_tracking(mode):
+    """The attention kernel folds the softmax reference into the Q K^T accumulator one tile ahead and only checks row
+    sums on its fast path: scores that outgrow the reference (slowly, abruptly, by more than the fp16 range) must take
+    the rescale / exact-path branches and still match the fp32 softmax."""
+    Be, seq, H = 2, 700, 2
+    inner = H * 64
+    qkv = gen((Be * seq, 3 * inner), 23, 1.0).float().view(Be, seq, 3, H, 64)
+    pos = torch.arange(seq, device=DEV, dtype=torch.float32)[None, :, None, None]
+    if mode == "wide":       # logits with a standard deviation of ~13 (log2 units): large jumps between key tiles
+        qkv[:, :, 0] *= 3.0
+        qkv[:, :, 1] *= 3.0
+    elif mode == "rising":   # every key tile is larger than the one before
+        qkv[:, :, 1] *= 1.0 + pos / 128.0
+    elif mode == "falling":  # the first tile dominates: later probabilities underflow exactly like the reference's
+        qkv[:, :, 1] *= 6.0 / (1.0 + pos / 64.0)
+    elif mode == "spike":    # one key in the fifth tile with a score far above everything before it
+        qkv[:, :, 0] = qkv[:, :, 0].abs()
+        qkv[:, 600, 1] = 12.0
+    qkv = qkv.half().reshape(Be * seq, 3 * inner).contiguous()
+    out = ops.attention(qkv, Be, seq, H)
+    q, k, v = qkv.float().view(Be, seq, 3, H, 64).permute(2, 0, 3, 1, 4)
+    ref = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(Be * seq, inner)
+    report(f"attention reference tracking: {mode}", out, ref)
+    assert torch.isfinite(out.float()).all()
+    assert rel(out, ref) <= 5e-3  # one more fp16 rounding of the scaled queries shows at logits of this size
+
+
 @pytest.mark.parametrize("D", [1024, 512, 128])
 def test_row_norm(D):
     rows = 1000

@@ -1,6 +1,5 @@
 #!/bin/bash
-# scratch: short validation of the current working tree on one GPU
+# scratch script for the A/B experiment of the day
 mkdir -p gpurun_out
-echo "=== gpu tests"; timeout 600 python -m pytest tests/ -x -q -m gpu 2>&1 | tail -3 | tee gpurun_out/test_gpu.log
-echo "=== smoke"; timeout 200 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1 | tee gpurun_out/smoke.log
-echo "=== bench"; timeout 400 python bench.py 2> gpurun_out/bench.err | tee gpurun_out/bench.json | cut -c1-200
+timeout 600 ncu --set full --clock-control none --import-source on -k "regex:attn_fwd" -s 2 -c 1 -o gpurun_out/prof_attn_new -f python tools/ncu_attn.py > gpurun_out/ncu_attn_new.log 2>&1
+tail -3 gpurun_out/ncu_attn_new.log
