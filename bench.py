@@ -44,6 +44,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 import synthdata as SD  # noqa: E402  (neutral synthetic weights / inputs shared with the tests and the CPU oracle)
@@ -469,6 +470,25 @@ def extra_workloads(dev, world, rank, dist, barrier, models):
                          batched_ms=round(ms_b, 2), per_chunk_ms=round(ms_s, 2), speedup=round(ms_s / ms_b, 3),
                          value=round(frames / (ms_b * 1e-3), 1), unit="mel_frames/s",
                          note="host audio in, host waveform out; batched = one exact_varlen sampler call for all chunks"))
+        # request-level serving (Triton Python backend mirror, serving.py): 4 requests with different reference lengths
+        # and texts through ONE execute() (max_batch_size 4, as config.pbtxt) against one execute() per request
+        from f5_tts_b200 import serving as SRV
+
+        proc = SRV.F5TTSRequestProcessor(model, voc, device=dev, nfe_step=w2["nfe"])
+        wav_np = synth_inputs(w2)[0].numpy()
+        reqs = [dict(reference_wav=wav_np[:, : 24000 * s], reference_wav_len=np.array([24000 * s], np.int32),
+                     reference_text=ref_text[: 15 * s], target_text=(base + " " + base)[: 35 * s * k])
+                for s, k in ((3, 2), (2, 3), (3, 1), (2, 2))]
+        outs = proc.execute(reqs)
+        audio_s = sum(len(o) for o in outs) / 24000.0
+        ms_b = timed(lambda: proc.execute(reqs), 3, 1, barrier)
+        ms_s = timed(lambda: [proc.execute([r]) for r in reqs], 3, 1, barrier)
+        recs.append(dict(workload="serving: 4 requests (2-3 s reference, 7-14 s generated, NFE 32) through "
+                                  "serving.F5TTSRequestProcessor.execute (Triton Python backend contract)",
+                         generated_audio_s=round(audio_s, 2), n_gpus=1, steps=3, warmup=1, batched_ms=round(ms_b, 2),
+                         per_request_ms=round(ms_s, 2), speedup=round(ms_s / ms_b, 3), rtf=round(ms_b * 1e-3 / audio_s, 5),
+                         note="host numpy in, host numpy out; the reference publishes RTF 0.0394 for this contract on an "
+                              "L20 with TensorRT-LLM (other hardware, other prompts: not a baseline for vs_baseline)"))
     # cfg4: 64 fixed 10 s utterances, NFE 16, sharded by utterance over the ranks; batches of 8 per sampler call
     w = WORKLOADS["cfg4"]
     model, voc = models(w["arch"])

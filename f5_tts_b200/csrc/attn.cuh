@@ -141,6 +141,16 @@ __device__ __forceinline__ float row_max128(const uint32_t (&r0)[32], const uint
   return fmaxf(ma, mb);
 }
 
+__device__ __forceinline__ float row_max32(const uint32_t (&r)[32]) {
+  float ma = -INFINITY, mb = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 32; i += 4) {
+    ma = fmax3(ma, __uint_as_float(r[i]), __uint_as_float(r[i + 1]));
+    mb = fmax3(mb, __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
+  }
+  return fmaxf(ma, mb);
+}
+
 // scores of keys at or past kv_rem -> -inf (last key tile of a sample only)
 __device__ __forceinline__ void mask_tail32(uint32_t (&r)[32], int col0, int kv_rem) {
 #pragma unroll
@@ -312,13 +322,22 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnPar
 #endif
       tc_fence_before();
       mbar_arrive(&s_free[w]);  // S_w is in registers: the tensor core may overwrite it with the next tile's scores
-      if (kv_rem < kAttnBKV) {  // warp-uniform, last tile of the sample: one masking pass instead of a second code path
-        mask_tail32(r0, 0, kv_rem);
-        mask_tail32(r1, 32, kv_rem);
-        mask_tail32(r2, 64, kv_rem);
-        mask_tail32(r3, 96, kv_rem);
+      float mx;
+      if (kv_rem < kAttnBKV) {
+        // warp-uniform, last tile of the sample: only the 32-key chunk that straddles the end is masked element by
+        // element; chunks that lie wholly past the end are left out of the max and cost no exponentials below
+        // (the full masking pass was 256 instructions — a third of a tile's issue slots — on one tile in eight)
+        if (kv_rem < 32) mask_tail32(r0, 0, kv_rem);
+        else if (kv_rem < 64) mask_tail32(r1, 32, kv_rem);
+        else if (kv_rem < 96) mask_tail32(r2, 64, kv_rem);
+        else mask_tail32(r3, 96, kv_rem);
+        mx = row_max32(r0);
+        if (kv_rem > 32) mx = fmaxf(mx, row_max32(r1));
+        if (kv_rem > 64) mx = fmaxf(mx, row_max32(r2));
+        if (kv_rem > 96) mx = fmaxf(mx, row_max32(r3));
+      } else {
+        mx = row_max128(r0, r1, r2, r3);
       }
-      const float mx = row_max128(r0, r1, r2, r3);
       const float m_new = fmaxf(m_run, mx * p.scale_log2);
       // lazy rescale (warp-uniform decision because tcgen05.ld/st are warp-collective)
       const bool grow = (m_new - m_run) > 8.0f;  // also true on the first tile (m_run = -inf)

@@ -173,3 +173,44 @@ def test_packed_weight_cache_roundtrip(assets, tmp_path, golden_dir):
         Wt.packed_tensors = orig
     o1, _ = m1.sample(cond.half(), text, 150, **kw, y0=y0)
     assert torch.equal(o1, o2)
+
+
+def test_serving_requests_batched_equal_single(assets):
+    """serving.F5TTSRequestProcessor (Triton Python backend mirror, model.py:176-269): a batch of requests with different
+    reference lengths and texts goes through ONE sampler call (exact_varlen) and every answer is bit-identical to the
+    same request served alone; the single-request answer equals the reference's formulas on top of `CFM.sample`."""
+    from f5_tts_b200 import serving
+
+    a = assets
+    audio, sr = infer._load_wav(a["ref"])
+    wav = audio.numpy()
+    texts = ["I don't really care what you call me.", "Hello there.", "But always remember, I am mighty and enduring."]
+    reqs = [
+        {"reference_wav": wav, "reference_wav_len": np.array([wav.shape[1]], np.int32), "reference_text": REF_TEXT,
+         "target_text": texts[0]},
+        {"reference_wav": wav, "reference_wav_len": np.array([60000], np.int32),  # a shorter prompt out of the same file
+         "reference_text": "Some call me nature,", "target_text": texts[1]},
+        {"reference_wav": 0.2 * wav[:, :90000], "reference_text": np.array([[b"Some call me nature, others call me"]], dtype=object),
+         "target_text": texts[2]},
+    ]
+    proc = serving.F5TTSRequestProcessor(a["tts"].ema_model, a["tts"].vocoder, device=DEV, nfe_step=NFE, seed=11)
+    batched = proc.execute(reqs)
+    singles = [proc.execute([r])[0] for r in reqs]
+    for i, (b, s) in enumerate(zip(batched, singles)):
+        assert b.shape == s.shape and np.isfinite(b).all() and float(np.abs(b).max()) > 0
+        assert np.array_equal(b, s), f"request {i}: batched answer differs from the single-request answer"
+    # request 0 alone == the reference's formulas around a plain sampler call with the same seed
+    ref_len = 1 + wav.shape[1] // 256
+    est = int(ref_len * (1 + len(texts[0].encode()) / len(REF_TEXT.encode())))
+    model = a["tts"].ema_model
+    rms = float(torch.sqrt(torch.mean(torch.square(audio))))
+    w0 = audio * (0.1 / rms) if rms < 0.1 else audio
+    cond = model.mel_spec(w0.to(DEV), frames_last=False)
+    tok = infer.convert_char_to_pinyin([REF_TEXT + texts[0]])
+    out, _ = model.sample(cond=cond, text=tok, duration=est, steps=NFE, cfg_strength=2.0, sway_sampling_coef=-1.0, seed=11)
+    mel = out[:, ref_len:est, :].float().permute(0, 2, 1).contiguous()
+    w_ref = a["tts"].vocoder.decode(mel).squeeze(0)
+    if rms < 0.1:
+        w_ref = w_ref * rms / 0.1
+    assert len(singles[0]) == 256 * (est - ref_len - 1)
+    assert np.array_equal(singles[0], w_ref.cpu().numpy())
