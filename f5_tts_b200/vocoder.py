@@ -67,7 +67,11 @@ class Vocos(nn.Module):
                    padding=h.get("padding", "same"))
 
     def _pack(self):
-        fp = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        mods = self.__dict__.get("_param_modules")
+        if mods is None:  # the module tree is fixed after __init__; nn.Module.parameters() re-walks it on every call
+            mods = [m for m in self.modules() if m._parameters]
+            self.__dict__["_param_modules"] = mods
+        fp = tuple((p.data_ptr(), p._version) for m in mods for p in m._parameters.values() if p is not None)
         with self._lock:
             if self._packed is not None and self._packed["fp"] == fp:
                 return self._packed

@@ -1,6 +1,7 @@
 #!/bin/bash
 # scratch script for the A/B experiment of the day
 mkdir -p gpurun_out
-timeout 120 tools/microbench/mma_rate 2>&1 | tee gpurun_out/mma_rate.log
-timeout 600 python bench.py --steps 10 --warmup 3 --no-extras --no-cpu-baseline 2> gpurun_out/bench_q.err > gpurun_out/bench_q.json; python -c "
-import json; d=json.load(open('gpurun_out/bench_q.json')); print('value ms', d['ms_per_step'], 'e2e ms', d['e2e']['ms_per_step'], 'parity', d['parity']['rel_l2'])"
+timeout 600 python -m pytest tests/test_gpu_kernels.py -x -q -k "attention" 2>&1 | tail -3 | tee gpurun_out/test_attn.log
+timeout 900 python -m pytest tests/test_gpu_infer.py -x -q 2>&1 | tail -5 | tee gpurun_out/test_infer.log
+timeout 300 python tools/attn_bench.py 2>&1 | tail -8 | tee gpurun_out/attn_bench_prod.log
+timeout 1200 python bench.py --gpus 1 --steps 20 --warmup 5 2> gpurun_out/bench.err > gpurun_out/bench.json; cut -c1-400 gpurun_out/bench.json; tail -3 gpurun_out/bench.err | cut -c1-300
