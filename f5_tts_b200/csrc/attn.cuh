@@ -28,6 +28,15 @@
 #include "common.cuh"
 #include "kparams.h"
 
+// register split of the CTA's pool (384 threads x 168 registers): 128 x PRODUCER + 256 x SOFTMAX must not exceed it
+#ifndef F5_ATTN_REGS_PRODUCER
+#define F5_ATTN_REGS_PRODUCER 64
+#endif
+#ifndef F5_ATTN_REGS_SOFTMAX
+#define F5_ATTN_REGS_SOFTMAX 216
+#endif
+static_assert(128 * F5_ATTN_REGS_PRODUCER + 256 * F5_ATTN_REGS_SOFTMAX <= 384 * 168, "setmaxnreg split exceeds the CTA's pool");
+
 namespace f5 {
 
 __device__ __forceinline__ float ex2_approx(float x) {  // one MUFU.EX2; inputs are <= ~8, -inf -> 0
@@ -216,7 +225,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnPar
   const int n_kv = (kv_len + kAttnBKV - 1) / kAttnBKV;
 
   if (warp < 4) {
-  asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(F5_ATTN_REGS_PRODUCER));
   if (warp == 0) {
     if (elect_one()) {
       mbar_expect_tx(q_full, 2 * kAttnTile);
@@ -284,7 +293,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnPar
     }
   }
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(F5_ATTN_REGS_SOFTMAX));
     const int w = (warp - 4) >> 2;  // softmax warpgroup 0 / 1
     const int q = warp & 3;         // TMEM lane quarter
     const int row = q * 32 + int(lane_id());
