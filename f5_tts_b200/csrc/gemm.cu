@@ -335,6 +335,16 @@ int gemm_plan(GemmPlan* pl, const void* A, const void* W, const f5_gemm_args* a)
   p.skip_pad = (a->skip_padded_tiles && a->row_len != nullptr && a->seq > 0 && (conv || a->batches == 1)) ? 1 : 0;
   // a prefetched W tile belongs to the CTA's first tile: not known to be computed when padded tiles are skipped
   p.w_prefetch = (a->weights_static && !p.skip_pad) ? 1 : 0;
+#ifdef F5_TRACE
+  {  // instrumented build: F5_GEMM_TRACE=1 records per-CTA phase clocks of every launch (read back by f5_debug_gemm_trace)
+    static int want = -1;
+    if (want < 0) {
+      want = getenv("F5_GEMM_TRACE") ? 1 : 0;
+      if (want) cudaMalloc(&g_trace, sizeof(long long) * 16 * 4096);
+    }
+    p.dbg_ts = want ? g_trace : nullptr;
+  }
+#endif
   int rc;
   if (conv) {
     if (a->n_out % 64 || a->lda < a->n_out) {
