@@ -13,8 +13,8 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
     config.addinivalue_line("markers", "slow: longer CPU test")
-    config.addinivalue_line("markers", "fullsize: GPU parity at the real BASELINE.json sizes; the CPU oracle leg takes "
-                                       "about a minute per test on the box's host cores")
+    config.addinivalue_line("markers", "fullsize: GPU parity at the real BASELINE.json sizes against committed golden "
+                                       "vectors of the reference / oracle (tests/golden/cfg2_full_nfe32.npz, fullsize_*.npz)")
 
 
 @pytest.fixture(scope="session")
